@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- NT-Xent forward+backward throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path (normalise -> [all-gather] -> fused forward -> backward) over
+one synthetic batch.  Workload at every N: BASELINE.json's target configuration, global batch 32768
+pairs x d=128, tau=0.5, both inputs requiring grad, row-sharded over the N ranks (strong scaling);
+it fits one GPU because the 2Bx2B logit matrix is never materialised.  configs[1] (4096 pairs) is
+reported as a secondary number inside ``config`` at N=1.
+
+Prints ONE JSON line on rank 0 (see the keys below).  ``--impl reference`` times the reference's
+own CPU implementation of the path (the torch port in oracle/, all host threads) on a bounded
+sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ntxent_fwd_bwd_pairs_per_sec"
+UNIT = "pairs/s"
+PAIRS = 32768
+DIM = 128
+TAU = 0.5
+
+
+def workload_name(pairs, dim, tau):
+    return f"NT-Xent fwd+bwd, global batch {pairs} pairs, d={dim}, tau={tau}, both inputs require grad"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(bf16=float(p["bf16_tflops"]), bf16_sustained=float(p.get("bf16_tflops_sustained", 0)),
+                    hbm=float(p["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)")
+    except Exception:
+        return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), power_w_max=max(power),
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def run_reference(args, rank):
+    """CPU arm: the reference's own implementation (torch port) on all host threads."""
+    if rank != 0:
+        return
+    from oracle.cpu_baseline import time_port_stripe
+    import torch
+    b_sample = 256
+    r = time_port_stripe(PAIRS, DIM, TAU, b_sample, steps=args.steps, warmup=max(args.warmup, 2))
+    sample = (f"stripe of {r['b_sample']} anchor pairs x all {PAIRS} global keys per step, fwd+bwd "
+              f"(keys constant as in the reference's world_size>1 branch), torch {torch.__version__} fp32")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["pairs_per_s"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 2),
+        "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(PAIRS, DIM, TAU), "pairs_global": PAIRS, "dim": DIM,
+                   "temperature": TAU},
+        "cpu_baseline": {"value": r["pairs_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": r["pairs_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=PAIRS, help="global batch (pairs)")
+    ap.add_argument("--dim", type=int, default=DIM)
+    ap.add_argument("--tau", type=float, default=TAU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import maai_b200
+    from maai_b200.Objective import _Profiler
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = maai_b200._lib.load()
+    peaks = load_peaks()
+
+    B, d, tau = args.pairs, args.dim, args.tau
+    assert B % world == 0
+    b = B // world
+
+    def make_inputs(bb):
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        return (torch.randn(bb, d, generator=g, device=dev), torch.randn(bb, d, generator=g, device=dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(x, y):
+        x.grad = None
+        y.grad = None
+        loss, _, _ = maai_b200.contrastive_loss(x, y, temperature=tau, local_rank=rank, world_size=world,
+                                                device=dev)
+        loss.backward()
+        return loss
+
+    def timed_run(bb, steps, warmup, profile):
+        h1, h2 = make_inputs(bb)
+        x = h1.requires_grad_(True)
+        y = h2.requires_grad_(True)
+        for _ in range(warmup):
+            step(x, y)
+        barrier()
+        _Profiler.reset()
+        _Profiler.enabled = profile
+        launches0 = lib.maai_launch_count()
+        evs = []
+        for _ in range(steps):
+            flush_buf.fill_(1)  # flush L2 between timed iterations (outside the event bracket)
+            a = torch.cuda.Event(enable_timing=True)
+            e = torch.cuda.Event(enable_timing=True)
+            a.record()
+            loss = step(x, y)
+            e.record()
+            evs.append((a, e))
+        barrier()
+        _Profiler.enabled = False
+        launches = lib.maai_launch_count() - launches0
+        ms = [a.elapsed_time(e) for a, e in evs]
+        total_ms = sum(ms)
+        if world > 1:
+            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t)
+        spans = {k: [a.elapsed_time(e) for a, e in v] for k, v in _Profiler.events.items()}
+        return dict(ms_per_step=total_ms / steps, ms_median=statistics.median(ms), launches=launches,
+                    spans=spans, loss=float(loss))
+
+    # ---------------- main timed region (device-resident inputs) ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    main_r = timed_run(b, args.steps, args.warmup, profile=True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- end to end through the public API with HOST buffers ----------------
+    g = torch.Generator().manual_seed(1234 + rank)
+    hp1 = torch.randn(b, d, generator=g).pin_memory()
+    hp2 = torch.randn(b, d, generator=g).pin_memory()
+    out_g1 = torch.empty(b, d).pin_memory()
+    out_g2 = torch.empty(b, d).pin_memory()
+    out_loss = torch.empty(()).pin_memory()
+
+    def e2e_step():
+        x = hp1.to(dev, non_blocking=True).requires_grad_(True)
+        y = hp2.to(dev, non_blocking=True).requires_grad_(True)
+        loss, _, _ = maai_b200.contrastive_loss(x, y, temperature=tau, local_rank=rank, world_size=world,
+                                                device=dev)
+        loss.backward()
+        out_loss.copy_(loss.detach(), non_blocking=True)
+        out_g1.copy_(x.grad, non_blocking=True)
+        out_g2.copy_(y.grad, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the host results every step
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t)
+    e2e_pairs = B * args.steps / e2e_s
+    h2d = 2 * b * d * 4
+    d2h = 2 * b * d * 4 + 4
+
+    # ---------------- secondary: configs[1] (4096 pairs, 1 GPU) ----------------
+    secondary = None
+    if world == 1 and not args.no_secondary and B != 4096:
+        s = timed_run(4096, max(args.steps, 50), args.warmup, profile=False)
+        secondary = {"workload": workload_name(4096, d, tau), "ms_per_step": s["ms_per_step"],
+                     "pairs_per_s": 4096 / (s["ms_per_step"] * 1e-3),
+                     "frac_bf16_peak": 24.0 * 4096 ** 2 * d / (s["ms_per_step"] * 1e-3) / (peaks["bf16"] * 1e12)}
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.cpu_baseline import time_port_stripe
+        r = time_port_stripe(B, d, tau, 256, steps=10, warmup=2)
+        cpu = {"value": r["pairs_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+               "sample": f"10 steps of a stripe of {r['b_sample']} anchor pairs x all {B} global keys, fwd+bwd, "
+                         f"torch {torch.__version__} fp32 CPU ({r['s_per_step']:.3f} s/step)"}
+
+    if rank == 0:
+        ms = main_r["ms_per_step"]
+        value = B / (ms * 1e-3)
+        # dominant kernel: ntxent_tile_kernel<D, BWD> (recompute S + P.Z): algorithmic 16*b*B*d flops per
+        # launch (16 B^2 d of the 24 B^2 d per step are backward, split over the ranks)
+        bwd_ms = statistics.mean(main_r["spans"]["bwd"]) if main_r["spans"]["bwd"] else None
+        fwd_ms = statistics.mean(main_r["spans"]["fwd"]) if main_r["spans"]["fwd"] else None
+        flops_bwd = 16.0 * b * B * d
+        achieved = flops_bwd / (bwd_ms * 1e-3) / 1e12 if bwd_ms else None
+        step_tflops = 24.0 * B * B * d / (ms * 1e-3) / 1e12 / world
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(B, d, tau), "pairs_global": B, "pairs_per_gpu": b,
+                       "dim": d, "temperature": tau,
+                       "parallelism": f"dp{world}: anchor rows sharded, bf16 all-gather of z, fp32 all-gather of row factors",
+                       "l2": "flushed between timed steps (256 MiB write outside the event bracket)",
+                       "step_tflops_per_gpu_algorithmic": step_tflops,
+                       "step_frac_bf16_peak": step_tflops / peaks["bf16"],
+                       "ms_median": main_r["ms_median"], "loss": main_r["loss"],
+                       "fwd_call_ms": fwd_ms, "bwd_call_ms": bwd_ms},
+            "clocks": clocks,
+            "e2e": {"value": e2e_pairs, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s / args.steps * 1e3,
+                    "what": "pinned host h1,h2 -> device, contrastive_loss + backward, loss + dh1 + dh2 -> pinned host, wall clock"},
+            "gpu_launches": int(main_r["launches"]),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
+                         "frac": (achieved / peaks["bf16"]) if achieved else None, "traffic": None,
+                         "kernel": f"ntxent_tile_kernel<{maai_b200.padded_dim(d)},BWD>",
+                         "how": "16*b*B*d algorithmic flops / mean CUDA-event time of the maai_ntxent_bwd call "
+                                "(memset + tile kernel + dh kernel) over the timed steps",
+                         "peak_source": peaks["source"] + ", burst cuBLAS bf16",
+                         "peak_sustained": peaks["bf16_sustained"]},
+            "cpu_baseline": cpu,
+        }
+        if secondary:
+            line["config"]["configs1_4096_pairs"] = secondary
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,98 @@
+/* C ABI of the B200-native NT-Xent path (libmaai_ntxent.so).
+ *
+ * Drop-in boundary for /root/reference/SimCLR/Objective.py::contrastive_loss (Objective.py:17-81,
+ * helpers :102-125) and the autograd replay it triggers (Contrastive_Learning.py:698).  The
+ * Python host (multimodal-active-ai_b200/Objective.py) binds these with ctypes; INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name says host; nothing is allocated, freed or
+ *     synchronised inside the library; every call only enqueues work on `stream`
+ *     (a cudaStream_t passed as void*), so all calls are CUDA-graph capturable;
+ *   - return value: 0 ok, MAAI_E_ARG bad argument, MAAI_E_SHAPE unsupported shape,
+ *     MAAI_E_CUDA CUDA failure (text in maai_last_error());
+ *   - b = pairs owned by this rank, world = ranks, B = world*b, rows are laid out rank-major:
+ *     global row (p, v, k) = p*2b + v*b + k  (v = 0: hidden1 / view a, v = 1: hidden2 / view b),
+ *     i.e. exactly the order of an all-gather of each rank's stacked (2b, d_pad) block.  The
+ *     positive of a row is the other view of the same (p, k)  (labels_idx + rank*b, Objective.py:55).
+ *   - d_pad = maai_padded_dim(d) in {64, 128, 256}; z rows are zero-padded to d_pad.
+ */
+#ifndef MAAI_NTXENT_H_
+#define MAAI_NTXENT_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAAI_ABI_VERSION 1
+
+#define MAAI_OK 0
+#define MAAI_E_ARG (-1)
+#define MAAI_E_SHAPE (-2)
+#define MAAI_E_CUDA (-3)
+
+/* element type of hidden1 / hidden2 / dh1 / dh2 */
+#define MAAI_DT_F32 0
+#define MAAI_DT_BF16 1
+#define MAAI_DT_F16 2
+
+int maai_abi_version(void);
+const char* maai_last_error(void);
+
+/* Padded embedding width used by the tile kernels: 64, 128 or 256; MAAI_E_SHAPE if d < 1 or d > 256. */
+int maai_padded_dim(int d);
+
+/* Number of floats the `r_glob` array of maai_ntxent_bwd must hold: world*2b rounded up to 128. */
+size_t maai_ntxent_r_len(int b, int world);
+
+/* K1 -- replaces F.normalize x2 (Objective.py:41-43) and the fp32 send buffers of
+ * _cross_replica_concat (Objective.py:112).
+ *   h1, h2     (b, d) row-major contiguous, dtype in_dtype
+ *   z_out      (2b, d_pad) bf16: rows [0,b) = normalised h1, rows [b,2b) = normalised h2; pass the
+ *              address of this rank's slot of the (world, 2b, d_pad) gather buffer
+ *   inv_norm   (2b) fp32   1 / max(||h||, 1e-12)
+ *   pos_cos    (b)  fp32   cosine of each positive pair computed from the bf16 rows */
+int maai_ntxent_normalize(const void* h1, const void* h2, int b, int d, int in_dtype, void* z_out,
+                          float* inv_norm, float* pos_cos, void* stream);
+
+/* K2 -- replaces the four matmuls, /temperature, the LARGE_NUM self-mask, cat + log_softmax and the
+ * masked sum (Objective.py:67-79, 123-125) for this rank's 2b anchor rows against all world*2b keys.
+ *   z_glob     (world*2b, d_pad) bf16, gathered rows (for world == 1 the K1 output itself)
+ *   pos_cos    (b) from K1
+ *   rowsum_l   (2b) out: l_i = sum_{j != i} exp((z_i.z_j - 1) / tau)
+ *   r_out      (2b) out, may be NULL: 1 / (b * l_i), the row factor the backward needs
+ *   loss_out   (1)  out: this rank's loss, exactly Objective.py:79 */
+int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
+                    const float* pos_cos, float* rowsum_l, float* r_out, float* loss_out,
+                    void* stream);
+
+/* K3 + K4 -- replaces loss.backward() through Objective.py:41-79 (Contrastive_Learning.py:698).
+ *   dZ_i = (1/tau) [ sum_j E_ij (r_row_i + r_col_j) z_j - pos_coef * z_pos(i) ]   (i: this rank's anchors)
+ * (the j = pos(i) term and pos_coef are combined in fp32, outside the bf16 MMA: their difference
+ * is the positive's softmax-minus-target residual and must not be rounded to bf16)
+ * Full gradient (query side + key side) of sum_ranks loss_rank w.r.t. this rank's inputs, computed
+ * rank-locally from the symmetry of E: r_row = this rank's r_out, r_col = all-gathered r_out of every
+ * rank, pos_coef = 2/b.  The reference's world_size > 1 semantics (keys detached by the
+ * non-differentiable all_gather, Objective.py:112-114): r_col = zeros, pos_coef = 1/b.
+ *   r_row      (2b) floats
+ *   r_col      maai_ntxent_r_len(b, world) floats, zero padded
+ *   pos_cos    (b) from K1
+ *   grad_loss  (1) fp32 device scalar: upstream gradient of the loss
+ *   need_mask  bit 0: dh1 wanted, bit 1: dh2 wanted (hidden1 is detached in the reference's
+ *              training loop, Contrastive_Learning.py:685)
+ *   dh1, dh2   (b, d) dtype in_dtype, written only when the matching bit is set (may be NULL otherwise)
+ *   dz_acc     (2b, d_pad) fp32 scratch */
+int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, float pos_coef,
+                    const float* pos_cos, const void* h1, const void* h2, int in_dtype,
+                    const float* inv_norm, const float* grad_loss, int b, int world, int rank, int d, int d_pad,
+                    float inv_tau, int need_mask, void* dh1, void* dh2, float* dz_acc, void* stream);
+
+/* Kernel launches enqueued by this library since load (bench.py's gpu_launches claim). */
+unsigned long long maai_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAAI_NTXENT_H_ */

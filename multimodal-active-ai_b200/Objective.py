@@ -1,0 +1,232 @@
+"""B200-native drop-in for /root/reference/SimCLR/Objective.py.
+
+``contrastive_loss`` keeps the reference signature and return tuple (Objective.py:17-22, :81):
+
+    loss, logits_ab, labels = contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0,
+                                               local_rank=0, world_size=1, device='cpu')
+
+but the work is done by hand-written sm_100a kernels reached through the C ABI in
+include/maai_ntxent.h: one normalise+cast pass, one fused tcgen05 stripe kernel that never writes
+a logit to HBM, and a recompute-based backward.  PyTorch is only plumbing here (device memory,
+streams, autograd hook, torch.distributed for the embedding all-gather).
+
+Differences from the reference, all deliberate:
+  * ``logits_ab`` / ``labels`` (used only by validate(), Contrastive_Learning.py:860-868) are
+    produced only when autograd is disabled or ``return_logits=True``; the training path returns
+    ``None`` for them instead of materialising (b, B) fp32 + (b, 2B) int64 tensors every step.
+  * ``world_size > 1``: the reference's ``dist.all_gather`` is not differentiable, so it silently
+    drops the key-side gradient (Objective.py:112-114).  Here the gradient is the full one (query
+    side + key side) unless ``key_grad=False`` is passed.
+  * ``hidden_norm=False`` is not supported (no caller uses it; the fixed-maximum logsumexp needs
+    unit-norm rows) and raises ``NotImplementedError``.
+  * CPU tensors raise: there is no CPU / eager fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+LARGE_NUM = 1e9  # kept for API parity with Objective.py:6 (the fused kernels mask by predicate)
+MIN_TEMPERATURE = 0.02  # fixed-maximum logsumexp: exp((cos-1)/tau) must stay a normal fp32 for cos >= -1
+
+_DTYPES = {torch.float32: _lib.DT_F32, torch.bfloat16: _lib.DT_BF16, torch.float16: _lib.DT_F16}
+
+
+class _Profiler:
+    """Optional CUDA-event brackets around the C-ABI calls (bench.py's live per-kernel timing)."""
+    enabled = False
+    events = {"normalize": [], "fwd": [], "bwd": []}
+
+    @classmethod
+    def reset(cls):
+        for v in cls.events.values():
+            v.clear()
+
+    class span:
+        def __init__(self, name):
+            self.name = name
+
+        def __enter__(self):
+            if _Profiler.enabled:
+                self.a = torch.cuda.Event(enable_timing=True)
+                self.b = torch.cuda.Event(enable_timing=True)
+                self.a.record()
+            return self
+
+        def __exit__(self, *exc):
+            if _Profiler.enabled:
+                self.b.record()
+                _Profiler.events[self.name].append((self.a, self.b))
+            return False
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def padded_dim(d: int) -> int:
+    dp = _lib.load().maai_padded_dim(int(d))
+    if dp < 0:
+        raise ValueError(f"embedding dim {d} unsupported: the sm_100a tile kernels take 1 <= d <= 256")
+    return dp
+
+
+class _NTXentFunction(torch.autograd.Function):
+    """loss = NT-Xent(hidden1, hidden2) for this rank (Objective.py:79), autograd-compatible."""
+
+    @staticmethod
+    def forward(ctx, hidden1, hidden2, temperature, rank, world, group, key_grad, stash):
+        lib = _lib.load()
+        b, d = hidden1.shape
+        dev = hidden1.device
+        dp = padded_dim(d)
+        h1 = hidden1.contiguous()
+        h2 = hidden2.contiguous()
+        dt = _DTYPES[h1.dtype]
+        inv_tau = 1.0 / float(temperature)
+
+        z_all = torch.empty((world, 2 * b, dp), dtype=torch.bfloat16, device=dev)
+        inv_norm = torch.empty(2 * b, dtype=torch.float32, device=dev)
+        pos_cos = torch.empty(b, dtype=torch.float32, device=dev)
+        rowsum = torch.empty(2 * b, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        needs_grad = any(ctx.needs_input_grad[:2])
+        r_len = lib.maai_ntxent_r_len(b, world)
+        full = bool(key_grad) or world == 1
+        r_col = torch.zeros(r_len, dtype=torch.float32, device=dev) if needs_grad else None
+        if needs_grad and full:
+            r_row = r_col[rank * 2 * b:(rank + 1) * 2 * b]  # this rank's slot of the gathered factors
+        elif needs_grad:
+            r_row = torch.empty(2 * b, dtype=torch.float32, device=dev)  # keys detached: r_col stays 0
+        else:
+            r_row = None
+
+        with _Profiler.span("normalize"):
+            _lib.check(lib.maai_ntxent_normalize(_ptr(h1), _ptr(h2), b, d, dt, _ptr(z_all[rank]),
+                                                 _ptr(inv_norm), _ptr(pos_cos), _stream()),
+                       "maai_ntxent_normalize")
+        if world > 1:
+            # one bf16 all-gather of the stacked (2b, dp) block replaces the two fp32 list
+            # all_gathers of Objective.py:52-53, in place into the (world, 2b, dp) buffer
+            dist.all_gather_into_tensor(z_all.view(-1), z_all[rank].view(-1), group=group)
+        with _Profiler.span("fwd"):
+            _lib.check(lib.maai_ntxent_fwd(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(pos_cos),
+                                           _ptr(rowsum), _ptr(r_row), _ptr(loss), _stream()),
+                       "maai_ntxent_fwd")
+        if needs_grad:
+            if world > 1 and full:
+                # the backward needs every key's factor r_j = 1/(b l_j): 8b bytes per rank, in place
+                dist.all_gather_into_tensor(r_col[:world * 2 * b], r_row, group=group)
+            ctx.save_for_backward(h1, h2, z_all, inv_norm, r_row, r_col, pos_cos)
+            ctx.cfg = (b, d, dp, dt, inv_tau, rank, world, full)
+        if stash is not None:
+            stash["z_all"] = z_all
+            stash["rowsum"] = rowsum
+            stash["pos_cos"] = pos_cos
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        lib = _lib.load()
+        h1, h2, z_all, inv_norm, r_row, r_col, pos_cos = ctx.saved_tensors
+        b, d, dp, dt, inv_tau, rank, world, full = ctx.cfg
+        need = (1 if ctx.needs_input_grad[0] else 0) | (2 if ctx.needs_input_grad[1] else 0)
+        dev = h1.device
+        g = grad_loss.to(device=dev, dtype=torch.float32).contiguous()
+        dh1 = torch.empty_like(h1) if need & 1 else None
+        dh2 = torch.empty_like(h2) if need & 2 else None
+        dz_acc = torch.empty((2 * b, dp), dtype=torch.float32, device=dev)
+        pos_coef = (2.0 if full else 1.0) / b
+        with _Profiler.span("bwd"):
+            _lib.check(lib.maai_ntxent_bwd(_ptr(z_all), _ptr(r_row), _ptr(r_col), pos_coef,
+                                           _ptr(pos_cos), _ptr(h1), _ptr(h2), dt, _ptr(inv_norm),
+                                           _ptr(g), b, world, rank, d, dp, inv_tau, need, _ptr(dh1),
+                                           _ptr(dh2), _ptr(dz_acc), _stream()),
+                       "maai_ntxent_bwd")
+        return dh1, dh2, None, None, None, None, None, None
+
+
+def _validate(hidden1, hidden2, hidden_norm, temperature, world_size, local_rank):
+    if hidden1.shape != hidden2.shape:
+        raise AssertionError(f"hidden1.shape {tuple(hidden1.shape)} != hidden2.shape "
+                             f"{tuple(hidden2.shape)}")  # Objective.py:45
+    if hidden1.dim() != 2:
+        raise ValueError("hidden1/hidden2 must be (bsz, dim)")
+    if not hidden_norm:
+        raise NotImplementedError("hidden_norm=False is not supported by the fused sm_100a path "
+                                  "(fixed-maximum logsumexp needs unit-norm rows); no reference "
+                                  "caller uses it")
+    if not hidden1.is_cuda or not hidden2.is_cuda:
+        raise RuntimeError("maai NT-Xent runs on CUDA (sm_100a) tensors only: there is no CPU fallback")
+    if hidden1.dtype not in _DTYPES or hidden2.dtype != hidden1.dtype:
+        raise TypeError("hidden1/hidden2 must both be float32, bfloat16 or float16")
+    t = float(temperature)
+    if not (t >= MIN_TEMPERATURE) or not math.isfinite(t):
+        raise ValueError(f"temperature must be >= {MIN_TEMPERATURE} (got {temperature})")
+    if world_size < 1 or not (0 <= local_rank < world_size):
+        raise ValueError("need 0 <= local_rank < world_size")
+    if hidden1.shape[0] < 1:
+        raise ValueError("empty batch")
+
+
+def contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0, local_rank=0, world_size=1,
+                     device="cpu", *, group=None, key_grad=True, return_logits=None, _stash=None):
+    """Drop-in for Objective.contrastive_loss (Objective.py:17-81).
+
+    Args (reference): hidden1, hidden2 (bsz, dim); hidden_norm; temperature; local_rank (really the
+      global rank, Contrastive_Learning.py:688); world_size; device (ignored: the tensors' device).
+    Extra keyword-only args: ``group`` process group for the gathers; ``key_grad`` see module doc;
+      ``return_logits`` force (True) / suppress (False) the (logits_ab, labels) outputs, default:
+      only when autograd is disabled (the validate() path).
+
+    Returns (loss, logits_ab, labels) like the reference.
+    """
+    _validate(hidden1, hidden2, hidden_norm, temperature, world_size, local_rank)
+    stash = _stash
+    want_logits = (not torch.is_grad_enabled()) if return_logits is None else bool(return_logits)
+    if want_logits and stash is None:
+        stash = {}
+    loss = _NTXentFunction.apply(hidden1, hidden2, float(temperature), int(local_rank),
+                                 int(world_size), group, key_grad, stash)
+    logits_ab = labels = None
+    if want_logits:
+        logits_ab, labels = _logits_and_labels(stash["z_all"], hidden1.shape[0], int(local_rank),
+                                               int(world_size), float(temperature))
+    return loss, logits_ab, labels
+
+
+def _logits_and_labels(z_all, b, rank, world, temperature):
+    """validate()-only outputs (Contrastive_Learning.py:860-868): logits_ab = z1 . Z2^T / tau
+    (Objective.py:73) from the normalised bf16 rows, labels = one_hot(rank*b + k, 2B) (Objective.py:57)."""
+    z1 = z_all[rank, :b].float()
+    z2_all = z_all[:, b:].reshape(world * b, -1).float()
+    logits_ab = torch.matmul(z1, z2_all.t()) / temperature
+    idx = torch.arange(b, device=z_all.device) + rank * b
+    labels = torch.nn.functional.one_hot(idx, 2 * world * b)
+    return logits_ab, labels
+
+
+class NTXentLoss(torch.nn.Module):
+    """Module form of :func:`contrastive_loss` holding temperature / rank / world / group."""
+
+    def __init__(self, temperature=1.0, local_rank=0, world_size=1, group=None, key_grad=True):
+        super().__init__()
+        self.temperature = float(temperature)
+        self.local_rank = int(local_rank)
+        self.world_size = int(world_size)
+        self.group = group
+        self.key_grad = key_grad
+
+    def forward(self, hidden1, hidden2):
+        return contrastive_loss(hidden1, hidden2, True, self.temperature, self.local_rank,
+                                self.world_size, hidden1.device, group=self.group,
+                                key_grad=self.key_grad)[0]

@@ -1,0 +1,66 @@
+"""ctypes binding of include/maai_ntxent.h.  There is no fallback: if the CUDA library is missing
+or a call fails, the caller gets an exception."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmaai_ntxent.so")
+
+ABI_VERSION = 1
+OK, E_ARG, E_SHAPE, E_CUDA = 0, -1, -2, -3
+DT_F32, DT_BF16, DT_F16 = 0, 1, 2
+
+_c_int, _c_float, _c_void_p, _c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+# name -> (restype, argtypes): every symbol declared in include/maai_ntxent.h
+SIGNATURES = {
+    "maai_abi_version": (_c_int, []),
+    "maai_last_error": (ctypes.c_char_p, []),
+    "maai_padded_dim": (_c_int, [_c_int]),
+    "maai_ntxent_r_len": (_c_size_t, [_c_int, _c_int]),
+    "maai_ntxent_normalize": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p,
+                                       _c_void_p, _c_void_p, _c_void_p]),
+    "maai_ntxent_fwd": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p,
+                                 _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "maai_ntxent_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_float, _c_void_p, _c_void_p, _c_void_p,
+                                 _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                 _c_float, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "maai_launch_count": (ctypes.c_ulonglong, []),
+}
+
+_lib = None
+
+
+class MaaiError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load libmaai_ntxent.so (built by build.py / __graft_entry__.build()).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MaaiError(
+            f"{LIB_PATH} not found: the sm_100a CUDA library has not been built "
+            "(run `python multimodal-active-ai_b200/build.py`). There is no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    if lib.maai_abi_version() != ABI_VERSION:
+        raise MaaiError(f"ABI mismatch: library {lib.maai_abi_version()} != binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc == OK:
+        return
+    msg = load().maai_last_error().decode("utf-8", "replace")
+    if rc in (E_ARG, E_SHAPE):
+        raise ValueError(f"{what}: {msg}")
+    raise MaaiError(f"{what}: {msg}")

@@ -1,0 +1,281 @@
+// C ABI (include/maai_ntxent.h) over the sm_100a NT-Xent kernels.  Host side only builds TMA
+// descriptors and enqueues kernels on the caller's stream: no allocation, no synchronisation.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/maai_ntxent.h"
+#include "ntxent_aux.cuh"
+#include "ntxent_tile.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(const char* what, cudaError_t e) {
+  return fail(MAAI_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define MAAI_CUDA(call)                                  \
+  do {                                                   \
+    cudaError_t _e = (call);                             \
+    if (_e != cudaSuccess) return cuda_fail(#call, _e);  \
+  } while (0)
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// bf16 (rows, d_pad) row-major -> boxes of 128 rows x 64 columns (128 B), 128-byte swizzle
+int make_rows_tmap(CUtensorMap* m, const void* base, int rows, int d_pad) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(MAAI_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[96];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (CUresult %d), rows=%d d_pad=%d", int(r),
+             rows, d_pad);
+    return fail(MAAI_E_CUDA, buf);
+  }
+  return MAAI_OK;
+}
+
+int sm_count() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return v;
+  }();
+  return n;
+}
+
+template <int D, bool BWD>
+int launch_tile(const void* q_base, int m_loc, const void* k_base, int m_glob, int row_global_base,
+                float inv_tau, const float* r_row, const float* r_col, float* l_out, float* dz_acc,
+                int pos_split, int pos_delta, cudaStream_t s) {
+  using C = maai::TileCfg<D, BWD>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(maai::ntxent_tile_kernel<D, BWD>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(smem)", attr_err);
+  CUtensorMap tq, tk;
+  int rc;
+  if ((rc = make_rows_tmap(&tq, q_base, m_loc, D)) != MAAI_OK) return rc;
+  if ((rc = make_rows_tmap(&tk, k_base, m_glob, D)) != MAAI_OK) return rc;
+  maai::TileParams p;
+  p.m_loc = m_loc;
+  p.m_glob = m_glob;
+  p.row_global_base = row_global_base;
+  p.pos_split = pos_split;
+  p.pos_delta = pos_delta;
+  p.nrb = (m_loc + C::RB_ROWS - 1) / C::RB_ROWS;
+  p.nkt = (m_glob + C::KT - 1) / C::KT;
+  p.c1 = inv_tau * 1.4426950408889634f;
+  p.r_row = r_row;
+  p.r_col = r_col;
+  p.l_out = l_out;
+  p.dz_acc = dz_acc;
+  // MN-major SW128 operand: LBO = distance between 64-column chunks, SBO = between 8-row groups
+  static const uint32_t pv_lbo = getenv("MAAI_DEBUG_PV_LBO") ? atoi(getenv("MAAI_DEBUG_PV_LBO")) : C::CHUNK_BYTES;
+  static const uint32_t pv_sbo = getenv("MAAI_DEBUG_PV_SBO") ? atoi(getenv("MAAI_DEBUG_PV_SBO")) : 1024;
+  p.pv_lbo = pv_lbo;
+  p.pv_sbo = pv_sbo;
+  const long long items = (long long)p.nrb * p.nkt;
+  int sms = sm_count();
+  if (sms <= 0) return fail(MAAI_E_CUDA, "no CUDA device");
+  const int grid = (int)(items < sms ? items : sms);
+  maai::ntxent_tile_kernel<D, BWD><<<grid, C::NTHREADS, C::SMEM_BYTES, s>>>(tq, tk, p);
+  ++g_launches;
+  MAAI_CUDA(cudaGetLastError());
+  return MAAI_OK;
+}
+
+template <bool BWD>
+int dispatch_tile(int d_pad, const void* q_base, int m_loc, const void* k_base, int m_glob,
+                  int row_global_base, float inv_tau, const float* r_row, const float* r_col,
+                  float* l_out, float* dz_acc, int pos_split, int pos_delta, cudaStream_t s) {
+  switch (d_pad) {
+    case 64:
+      return launch_tile<64, BWD>(q_base, m_loc, k_base, m_glob, row_global_base, inv_tau, r_row,
+                                  r_col, l_out, dz_acc, pos_split, pos_delta, s);
+    case 128:
+      return launch_tile<128, BWD>(q_base, m_loc, k_base, m_glob, row_global_base, inv_tau, r_row,
+                                   r_col, l_out, dz_acc, pos_split, pos_delta, s);
+    case 256:
+      return launch_tile<256, BWD>(q_base, m_loc, k_base, m_glob, row_global_base, inv_tau, r_row,
+                                   r_col, l_out, dz_acc, pos_split, pos_delta, s);
+    default:
+      return fail(MAAI_E_SHAPE, "d_pad must be 64, 128 or 256");
+  }
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_common(int b, int world, int rank) {
+  if (b < 1) return fail(MAAI_E_ARG, "b must be >= 1");
+  if (world < 1 || rank < 0 || rank >= world) return fail(MAAI_E_ARG, "need 0 <= rank < world");
+  if ((long long)b * 2 * world > (1ll << 30)) return fail(MAAI_E_SHAPE, "world*2b exceeds 2^30 rows");
+  return MAAI_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int maai_abi_version(void) { return MAAI_ABI_VERSION; }
+const char* maai_last_error(void) { return g_err.c_str(); }
+unsigned long long maai_launch_count(void) { return g_launches.load(); }
+
+int maai_padded_dim(int d) {
+  if (d < 1 || d > 256) return MAAI_E_SHAPE;
+  return d <= 64 ? 64 : (d <= 128 ? 128 : 256);
+}
+
+size_t maai_ntxent_r_len(int b, int world) {
+  const size_t m = (size_t)2 * b * world;
+  return (m + 127) / 128 * 128;
+}
+
+int maai_ntxent_normalize(const void* h1, const void* h2, int b, int d, int in_dtype, void* z_out,
+                          float* inv_norm, float* pos_cos, void* stream) {
+  if (!h1 || !h2 || !z_out || !inv_norm || !pos_cos) return fail(MAAI_E_ARG, "null pointer");
+  if (b < 1) return fail(MAAI_E_ARG, "b must be >= 1");
+  const int dp = maai_padded_dim(d);
+  if (dp < 0) return fail(MAAI_E_SHAPE, "embedding dim must be in [1, 256]");
+  if (!aligned16(z_out)) return fail(MAAI_E_ARG, "z_out must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int wpb = 8;
+  const int grid = (b + wpb - 1) / wpb;
+  auto* z = static_cast<__nv_bfloat16*>(z_out);
+  switch (in_dtype) {
+    case MAAI_DT_F32:
+      maai::normalize_cast_kernel<float><<<grid, wpb * 32, 0, s>>>(
+          static_cast<const float*>(h1), static_cast<const float*>(h2), b, d, dp, z, inv_norm, pos_cos);
+      break;
+    case MAAI_DT_BF16:
+      maai::normalize_cast_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, s>>>(
+          static_cast<const __nv_bfloat16*>(h1), static_cast<const __nv_bfloat16*>(h2), b, d, dp, z,
+          inv_norm, pos_cos);
+      break;
+    case MAAI_DT_F16:
+      maai::normalize_cast_kernel<__half><<<grid, wpb * 32, 0, s>>>(
+          static_cast<const __half*>(h1), static_cast<const __half*>(h2), b, d, dp, z, inv_norm, pos_cos);
+      break;
+    default:
+      return fail(MAAI_E_ARG, "in_dtype must be MAAI_DT_F32, MAAI_DT_BF16 or MAAI_DT_F16");
+  }
+  ++g_launches;
+  MAAI_CUDA(cudaGetLastError());
+  return MAAI_OK;
+}
+
+int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
+                    const float* pos_cos, float* rowsum_l, float* r_out, float* loss_out,
+                    void* stream) {
+  if (!z_glob || !pos_cos || !rowsum_l || !loss_out) return fail(MAAI_E_ARG, "null pointer");
+  int rc = check_common(b, world, rank);
+  if (rc != MAAI_OK) return rc;
+  if (!(inv_tau > 0.f)) return fail(MAAI_E_ARG, "temperature must be positive");
+  if (!aligned16(z_glob)) return fail(MAAI_E_ARG, "z_glob must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int m_loc = 2 * b, m_glob = 2 * b * world;
+  MAAI_CUDA(cudaMemsetAsync(rowsum_l, 0, sizeof(float) * m_loc, s));
+  const char* q_base = static_cast<const char*>(z_glob) + (size_t)rank * m_loc * d_pad * 2;
+  rc = dispatch_tile<false>(d_pad, q_base, m_loc, z_glob, m_glob, rank * m_loc, inv_tau, nullptr,
+                            nullptr, rowsum_l, nullptr, 0, 0, s);
+  if (rc != MAAI_OK) return rc;
+  maai::finalize_loss_kernel<<<1, 1024, 0, s>>>(rowsum_l, pos_cos, b, inv_tau, r_out, loss_out);
+  ++g_launches;
+  MAAI_CUDA(cudaGetLastError());
+  return MAAI_OK;
+}
+
+int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, float pos_coef,
+                    const float* pos_cos, const void* h1, const void* h2, int in_dtype,
+                    const float* inv_norm, const float* grad_loss, int b, int world, int rank, int d, int d_pad,
+                    float inv_tau, int need_mask, void* dh1, void* dh2, float* dz_acc, void* stream) {
+  if (!z_glob || !r_row || !r_col || !pos_cos || !h1 || !h2 || !inv_norm || !grad_loss || !dz_acc)
+    return fail(MAAI_E_ARG, "null pointer");
+  int rc = check_common(b, world, rank);
+  if (rc != MAAI_OK) return rc;
+  if (need_mask < 0 || need_mask > 3) return fail(MAAI_E_ARG, "need_mask must be in [0, 3]");
+  if (need_mask == 0) return MAAI_OK;
+  if (((need_mask & 1) && !dh1) || ((need_mask & 2) && !dh2)) return fail(MAAI_E_ARG, "null dh");
+  if (maai_padded_dim(d) != d_pad) return fail(MAAI_E_SHAPE, "d_pad does not match maai_padded_dim(d)");
+  if (!aligned16(z_glob) || !aligned16(r_col) || !aligned16(dz_acc))
+    return fail(MAAI_E_ARG, "z_glob, r_col and dz_acc must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int m_loc = 2 * b, m_glob = 2 * b * world;
+  // anchor rows that need a gradient: both views, or one contiguous view
+  const int row_begin = (need_mask == 2) ? b : 0;
+  const int rows = (need_mask == 3) ? m_loc : b;
+  float* acc = dz_acc + (size_t)row_begin * d_pad;
+  MAAI_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)rows * d_pad, s));
+  const char* q_base =
+      static_cast<const char*>(z_glob) + ((size_t)rank * m_loc + row_begin) * d_pad * 2;
+  rc = dispatch_tile<true>(d_pad, q_base, rows, z_glob, m_glob, rank * m_loc + row_begin, inv_tau,
+                           r_row + row_begin, r_col, nullptr, acc, b - row_begin, b, s);
+  if (rc != MAAI_OK) return rc;
+  const int wpb = 8;
+  const int grid = (rows + wpb - 1) / wpb;
+  switch (in_dtype) {
+    case MAAI_DT_F32:
+      maai::dh_kernel<float><<<grid, wpb * 32, 0, s>>>(
+          dz_acc, static_cast<const float*>(h1), static_cast<const float*>(h2), inv_norm, grad_loss, r_row,
+          r_col + (size_t)rank * m_loc, pos_cos, b, d, d_pad, inv_tau, pos_coef, need_mask, static_cast<float*>(dh1), static_cast<float*>(dh2));
+      break;
+    case MAAI_DT_BF16:
+      maai::dh_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, s>>>(
+          dz_acc, static_cast<const __nv_bfloat16*>(h1), static_cast<const __nv_bfloat16*>(h2),
+          inv_norm, grad_loss, r_row, r_col + (size_t)rank * m_loc, pos_cos, b, d, d_pad, inv_tau,
+          pos_coef, need_mask, static_cast<__nv_bfloat16*>(dh1),
+          static_cast<__nv_bfloat16*>(dh2));
+      break;
+    case MAAI_DT_F16:
+      maai::dh_kernel<__half><<<grid, wpb * 32, 0, s>>>(
+          dz_acc, static_cast<const __half*>(h1), static_cast<const __half*>(h2), inv_norm, grad_loss,
+          r_row, r_col + (size_t)rank * m_loc, pos_cos, b, d, d_pad, inv_tau, pos_coef, need_mask,
+          static_cast<__half*>(dh1), static_cast<__half*>(dh2));
+      break;
+    default:
+      return fail(MAAI_E_ARG, "in_dtype must be MAAI_DT_F32, MAAI_DT_BF16 or MAAI_DT_F16");
+  }
+  ++g_launches;
+  MAAI_CUDA(cudaGetLastError());
+  return MAAI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+// O(M d) side kernels of the NT-Xent path (HBM-bound, coalesced, one warp per row):
+//   normalize_cast_kernel  Objective.py:41-43  F.normalize -> bf16 z rows (+ 1/norm, positive cosine)
+//   finalize_loss_kernel   Objective.py:76-79  loss = (1/b) sum_i [ln l_i + (1 - cos_i,pos)/tau];  r = 1/(b l)
+//   dh_kernel              autograd tail: positive-pair term, 1/tau, grad_loss, F.normalize backward
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include "ptx_sm100.cuh"
+
+namespace maai {
+
+enum : int { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr float kNormEps = 1e-12f;  // F.normalize default eps (Objective.py:42-43)
+constexpr int kMaxPerLane = 8;      // d <= 256 -> at most 8 elements per lane
+
+// One warp per pair k: rows k (view a) and b + k (view b) of the rank-local z block.
+// z_out: (2b, DP) bf16, columns [d, DP) zero-filled so the padded tile MMA sees exact zeros.
+template <typename T>
+__global__ void __launch_bounds__(256)
+normalize_cast_kernel(const T* __restrict__ h1, const T* __restrict__ h2, int b, int d, int dp,
+                      __nv_bfloat16* __restrict__ z_out, float* __restrict__ inv_norm,
+                      float* __restrict__ pos_cos) {
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (k >= b) return;
+  float a[kMaxPerLane], c[kMaxPerLane];
+  float sa = 0.f, sc = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int e = lane + 32 * i;
+    a[i] = (e < d) ? to_f32<T>(h1[(size_t)k * d + e]) : 0.f;
+    c[i] = (e < d) ? to_f32<T>(h2[(size_t)k * d + e]) : 0.f;
+    sa += a[i] * a[i];
+    sc += c[i] * c[i];
+  }
+  sa = warp_sum(sa);
+  sc = warp_sum(sc);
+  const float ia = 1.f / fmaxf(sqrtf(sa), kNormEps);
+  const float ic = 1.f / fmaxf(sqrtf(sc), kNormEps);
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int e = lane + 32 * i;
+    if (e < dp) {
+      const __nv_bfloat16 za = __float2bfloat16_rn(a[i] * ia);
+      const __nv_bfloat16 zc = __float2bfloat16_rn(c[i] * ic);
+      z_out[(size_t)k * dp + e] = za;
+      z_out[(size_t)(b + k) * dp + e] = zc;
+      dot += __bfloat162float(za) * __bfloat162float(zc);  // same bf16 values the MMA multiplies
+    }
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) {
+    inv_norm[k] = ia;
+    inv_norm[b + k] = ic;
+    pos_cos[k] = dot;
+  }
+}
+
+// Single block, deterministic: loss = (1/b) * sum_{i < 2b} [ ln(l_i) + (1 - cos_pos(i)) / tau ]
+// (lse_i = 1/tau + ln l_i because E was taken relative to the fixed maximum 1/tau) and
+// r_i = 1 / (b * l_i) for the backward.  r_out may be null.
+__global__ void __launch_bounds__(1024)
+finalize_loss_kernel(const float* __restrict__ l, const float* __restrict__ pos_cos, int b,
+                     float inv_tau, float* __restrict__ r_out, float* __restrict__ loss_out) {
+  __shared__ double part[32];
+  double acc = 0.0;
+  const float inv_b = 1.f / float(b);
+  for (int i = threadIdx.x; i < 2 * b; i += blockDim.x) {
+    const float li = l[i];
+    const float cp = pos_cos[i < b ? i : i - b];
+    acc += double(logf(li) + (1.f - cp) * inv_tau);
+    if (r_out) r_out[i] = inv_b / li;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = (threadIdx.x < (blockDim.x >> 5)) ? part[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) *loss_out = float(v * double(inv_b));
+  }
+}
+
+// One warp per anchor row i of the views that need a gradient.
+//   dz_i = (g / tau) * (A_i + [E_i,pos (rr_i + rc_pos) - pos_coef] z_pos(i)),  A = dz_acc (fp32,
+//          stride dp, positive column excluded), pos_coef = 2/b (full gradient) or 1/b (query side
+//          only).  The bracket is the positive pair's softmax-minus-target coefficient, evaluated
+//          in fp32 from the same bf16 cosine the forward used.
+//   dh_i = inv_i * (dz_i - z_i (z_i . dz_i))       (rows with ||h|| < eps: dh = dz * inv)
+// z_i, z_pos are recomputed in fp32 from h (not the bf16 copies).
+template <typename T>
+__global__ void __launch_bounds__(256)
+dh_kernel(const float* __restrict__ dz_acc, const T* __restrict__ h1, const T* __restrict__ h2,
+          const float* __restrict__ inv_norm, const float* __restrict__ grad_loss,
+          const float* __restrict__ r_row, const float* __restrict__ r_col_loc,
+          const float* __restrict__ pos_cos, int b, int d, int dp, float inv_tau, float pos_coef,
+          int need_mask, T* __restrict__ dh1, T* __restrict__ dh2) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  // rows are enumerated over the views that need a gradient
+  const int both = (need_mask == 3);
+  const int nrows = both ? 2 * b : b;
+  if (w >= nrows) return;
+  const int i = both ? w : ((need_mask & 1) ? w : b + w);
+  const int view = i >= b;
+  const int k = view ? i - b : i;
+  const T* hi = (view ? h2 : h1) + (size_t)k * d;
+  const T* hp = (view ? h1 : h2) + (size_t)k * d;
+  const float inv_i = inv_norm[i];
+  const float inv_p = inv_norm[view ? k : b + k];
+  const float gs = grad_loss[0] * inv_tau;
+  const int ip = view ? k : b + k;  // local row of the positive
+  const float c1 = inv_tau * 1.4426950408889634f;
+  const float e_pos = ex2_approx(fmaf(pos_cos[k], c1, -c1));
+  const float cpos = e_pos * (r_row[i] + r_col_loc[ip]) - pos_coef;
+  float z[kMaxPerLane], dz[kMaxPerLane];
+  float dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxPerLane; ++j) {
+    const int e = lane + 32 * j;
+    if (e < d) {
+      z[j] = to_f32<T>(hi[e]) * inv_i;
+      const float zp = to_f32<T>(hp[e]) * inv_p;
+      dz[j] = gs * (dz_acc[(size_t)i * dp + e] + cpos * zp);
+      dot += z[j] * dz[j];
+    } else {
+      z[j] = 0.f;
+      dz[j] = 0.f;
+    }
+  }
+  dot = warp_sum(dot);
+  const bool clamped = inv_i >= 1.f / kNormEps;  // ||h|| < eps: z = h/eps, plain scaling
+  T* out = (view ? dh2 : dh1) + (size_t)k * d;
+#pragma unroll
+  for (int j = 0; j < kMaxPerLane; ++j) {
+    const int e = lane + 32 * j;
+    if (e < d) out[e] = from_f32<T>(inv_i * (clamped ? dz[j] : (dz[j] - z[j] * dot)));
+  }
+}
+
+}  // namespace maai

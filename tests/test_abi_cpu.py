@@ -1,0 +1,82 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol that
+include/maai_ntxent.h declares (no compute calls), and the host mirror validates arguments and
+refuses CPU tensors (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+import maai_b200
+from maai_b200 import _lib
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "maai_ntxent.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(maai_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 7
+    for n in names:
+        assert hasattr(lib, n), f"symbol {n} declared in include/maai_ntxent.h is not exported"
+    # and the binding covers exactly the declared set
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_abi_version_and_pure_host_helpers():
+    lib = _lib.load()
+    assert lib.maai_abi_version() == _lib.ABI_VERSION
+    assert [lib.maai_padded_dim(d) for d in (1, 20, 64, 65, 128, 129, 256)] == [64, 64, 64, 128, 128, 256, 256]
+    assert lib.maai_padded_dim(0) == _lib.E_SHAPE and lib.maai_padded_dim(257) == _lib.E_SHAPE
+    assert lib.maai_ntxent_r_len(100, 3) == 640 and lib.maai_ntxent_r_len(64, 1) == 128
+
+
+def test_c_abi_argument_errors_without_gpu():
+    lib = _lib.load()
+    # null pointers / bad sizes are rejected before any CUDA call
+    assert lib.maai_ntxent_normalize(None, None, 4, 8, 0, None, None, None, None) == _lib.E_ARG
+    assert b"null" in lib.maai_last_error()
+    assert lib.maai_ntxent_fwd(None, 4, 1, 0, 64, 1.0, None, None, None, None, None) == _lib.E_ARG
+    with pytest.raises(ValueError):
+        _lib.check(_lib.E_SHAPE, "x")
+    with pytest.raises(_lib.MaaiError):
+        _lib.check(_lib.E_CUDA, "x")
+
+
+def test_host_mirror_signature_matches_reference():
+    import inspect
+    sig = inspect.signature(maai_b200.contrastive_loss)
+    names = list(sig.parameters)
+    # Objective.py:17-22
+    assert names[:7] == ["hidden1", "hidden2", "hidden_norm", "temperature", "local_rank", "world_size", "device"]
+    p = sig.parameters
+    assert p["hidden_norm"].default is True and p["temperature"].default == 1.0
+    assert p["local_rank"].default == 0 and p["world_size"].default == 1 and p["device"].default == "cpu"
+
+
+def test_no_cpu_fallback_and_argument_validation():
+    a, b = torch.randn(4, 8), torch.randn(4, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        maai_b200.contrastive_loss(a, b)
+    with pytest.raises(AssertionError):  # Objective.py:45
+        maai_b200.contrastive_loss(a, torch.randn(5, 8))
+    with pytest.raises(NotImplementedError):
+        maai_b200.contrastive_loss(a, b, hidden_norm=False)
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through the oracle (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "multimodal-active-ai_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no CPU or PyTorch fallback", ""), f"{f} mentions oracle"
