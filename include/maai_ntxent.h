@@ -61,31 +61,32 @@ int maai_ntxent_normalize(const void* h1, const void* h2, int b, int d, int in_d
  * masked sum (Objective.py:67-79, 123-125) for this rank's 2b anchor rows against all world*2b keys.
  *   z_glob     (world*2b, d_pad) bf16, gathered rows (for world == 1 the K1 output itself)
  *   pos_cos    (b) from K1
- *   rowsum_l   (2b) out: l_i = sum_{j != i} exp((z_i.z_j - 1) / tau)
- *   r_out      (2b) out, may be NULL: 1 / (b * l_i), the row factor the backward needs
+ *   rowsum_l   (2b) out: l'_i = sum over the NEGATIVES j (j != i, j != pos(i)) of exp((z_i.z_j - 1)/tau);
+ *              the positive's term e_pos = exp((pos_cos - 1)/tau) is added in fp32 where needed
+ *   r_out      (2b) out, may be NULL: 1 / (b * (e_pos + l'_i)), the row factor the backward needs
  *   loss_out   (1)  out: this rank's loss, exactly Objective.py:79 */
 int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
                     const float* pos_cos, float* rowsum_l, float* r_out, float* loss_out,
                     void* stream);
 
 /* K3 + K4 -- replaces loss.backward() through Objective.py:41-79 (Contrastive_Learning.py:698).
- *   dZ_i = (1/tau) [ sum_j E_ij (r_row_i + r_col_j) z_j - pos_coef * z_pos(i) ]   (i: this rank's anchors)
- * (the j = pos(i) term and pos_coef are combined in fp32, outside the bf16 MMA: their difference
- * is the positive's softmax-minus-target residual and must not be rounded to bf16)
- * Full gradient (query side + key side) of sum_ranks loss_rank w.r.t. this rank's inputs, computed
- * rank-locally from the symmetry of E: r_row = this rank's r_out, r_col = all-gathered r_out of every
- * rank, pos_coef = 2/b.  The reference's world_size > 1 semantics (keys detached by the
- * non-differentiable all_gather, Objective.py:112-114): r_col = zeros, pos_coef = 1/b.
+ *   dZ_i = (1/tau) [ sum_{j != pos(i)} E_ij (r_row_i + r_col_j) z_j + cpos_i z_pos(i) ]   (i: this rank's anchors)
+ * cpos_i, the positive's softmax-minus-target coefficient, is formed in fp32 from rowsum_l and
+ * pos_cos, outside the bf16 MMA (it is a small residual when the softmax is peaked).
+ * key_grad = 1: full gradient (query side + key side) of sum_ranks loss_rank w.r.t. this rank's
+ * inputs, computed rank-locally from the symmetry of E: r_row = this rank's r_out, r_col =
+ * all-gathered r_out of every rank.  key_grad = 0: the reference's world_size > 1 semantics (keys
+ * detached by the non-differentiable all_gather, Objective.py:112-114): r_col = zeros.
  *   r_row      (2b) floats
  *   r_col      maai_ntxent_r_len(b, world) floats, zero padded
- *   pos_cos    (b) from K1
+ *   rowsum_l   (2b) from K2;  pos_cos (b) from K1
  *   grad_loss  (1) fp32 device scalar: upstream gradient of the loss
  *   need_mask  bit 0: dh1 wanted, bit 1: dh2 wanted (hidden1 is detached in the reference's
  *              training loop, Contrastive_Learning.py:685)
  *   dh1, dh2   (b, d) dtype in_dtype, written only when the matching bit is set (may be NULL otherwise)
  *   dz_acc     (2b, d_pad) fp32 scratch */
-int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, float pos_coef,
-                    const float* pos_cos, const void* h1, const void* h2, int in_dtype,
+int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, int key_grad,
+                    const float* rowsum_l, const float* pos_cos, const void* h1, const void* h2, int in_dtype,
                     const float* inv_norm, const float* grad_loss, int b, int world, int rank, int d, int d_pad,
                     float inv_tau, int need_mask, void* dh1, void* dh2, float* dz_acc, void* stream);
 

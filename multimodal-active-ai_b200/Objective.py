@@ -32,7 +32,7 @@ import torch.distributed as dist
 from . import _lib
 
 LARGE_NUM = 1e9  # kept for API parity with Objective.py:6 (the fused kernels mask by predicate)
-MIN_TEMPERATURE = 0.02  # fixed-maximum logsumexp: exp((cos-1)/tau) must stay a normal fp32 for cos >= -1
+MIN_TEMPERATURE = 0.025  # fixed-maximum logsumexp: exp((cos-1)/tau) must stay a normal fp32 for cos >= -1
 
 _DTYPES = {torch.float32: _lib.DT_F32, torch.bfloat16: _lib.DT_BF16, torch.float16: _lib.DT_F16}
 
@@ -80,6 +80,35 @@ def padded_dim(d: int) -> int:
     return dp
 
 
+def gather_rows(z_all: torch.Tensor, rank: int, group=None) -> torch.Tensor:
+    """All-gather of each rank's stacked (2b, d_pad) block of normalised rows, in place into the
+    (world, 2b, d_pad) buffer whose slot ``rank`` the caller has filled.  Replaces the two fp32 list
+    all_gathers + cat of _cross_replica_concat (Objective.py:52-53, 102-114) by ONE collective on
+    bf16 rows.  Global row order is rank-major: (p, view, k) -> p*2b + view*b + k."""
+    world = z_all.shape[0]
+    if world > 1:
+        dist.all_gather_into_tensor(z_all.view(-1), z_all[rank].reshape(-1), group=group)
+    return z_all
+
+
+def gather_row_factors(r_col: torch.Tensor, rank: int, b: int, world: int, group=None) -> torch.Tensor:
+    """All-gather of the per-anchor factors r = 1/(b (e_pos + l')) (2b fp32 per rank), in place:
+    slot ``rank`` of ``r_col`` (length >= world*2b) already holds this rank's values.  This is the
+    only backward-side exchange of the full-gradient path (symmetry identity)."""
+    if world > 1:
+        dist.all_gather_into_tensor(r_col[:world * 2 * b], r_col[rank * 2 * b:(rank + 1) * 2 * b],
+                                    group=group)
+    return r_col
+
+
+def positive_index(b: int, world: int) -> torch.Tensor:
+    """Global row index of every global row's positive under the rank-major layout (labels_idx +
+    rank*b of Objective.py:55 restated for stacked [view a; view b] blocks)."""
+    i = torch.arange(2 * b * world)
+    k = i % (2 * b)
+    return torch.where(k < b, i + b, i - b)
+
+
 class _NTXentFunction(torch.autograd.Function):
     """loss = NT-Xent(hidden1, hidden2) for this rank (Objective.py:79), autograd-compatible."""
 
@@ -114,19 +143,15 @@ class _NTXentFunction(torch.autograd.Function):
             _lib.check(lib.maai_ntxent_normalize(_ptr(h1), _ptr(h2), b, d, dt, _ptr(z_all[rank]),
                                                  _ptr(inv_norm), _ptr(pos_cos), _stream()),
                        "maai_ntxent_normalize")
-        if world > 1:
-            # one bf16 all-gather of the stacked (2b, dp) block replaces the two fp32 list
-            # all_gathers of Objective.py:52-53, in place into the (world, 2b, dp) buffer
-            dist.all_gather_into_tensor(z_all.view(-1), z_all[rank].view(-1), group=group)
+        gather_rows(z_all, rank, group)
         with _Profiler.span("fwd"):
             _lib.check(lib.maai_ntxent_fwd(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(pos_cos),
                                            _ptr(rowsum), _ptr(r_row), _ptr(loss), _stream()),
                        "maai_ntxent_fwd")
         if needs_grad:
-            if world > 1 and full:
-                # the backward needs every key's factor r_j = 1/(b l_j): 8b bytes per rank, in place
-                dist.all_gather_into_tensor(r_col[:world * 2 * b], r_row, group=group)
-            ctx.save_for_backward(h1, h2, z_all, inv_norm, r_row, r_col, pos_cos)
+            if full:
+                gather_row_factors(r_col, rank, b, world, group)
+            ctx.save_for_backward(h1, h2, z_all, inv_norm, r_row, r_col, pos_cos, rowsum)
             ctx.cfg = (b, d, dp, dt, inv_tau, rank, world, full)
         if stash is not None:
             stash["z_all"] = z_all
@@ -137,7 +162,7 @@ class _NTXentFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss):
         lib = _lib.load()
-        h1, h2, z_all, inv_norm, r_row, r_col, pos_cos = ctx.saved_tensors
+        h1, h2, z_all, inv_norm, r_row, r_col, pos_cos, rowsum = ctx.saved_tensors
         b, d, dp, dt, inv_tau, rank, world, full = ctx.cfg
         need = (1 if ctx.needs_input_grad[0] else 0) | (2 if ctx.needs_input_grad[1] else 0)
         dev = h1.device
@@ -145,10 +170,9 @@ class _NTXentFunction(torch.autograd.Function):
         dh1 = torch.empty_like(h1) if need & 1 else None
         dh2 = torch.empty_like(h2) if need & 2 else None
         dz_acc = torch.empty((2 * b, dp), dtype=torch.float32, device=dev)
-        pos_coef = (2.0 if full else 1.0) / b
         with _Profiler.span("bwd"):
-            _lib.check(lib.maai_ntxent_bwd(_ptr(z_all), _ptr(r_row), _ptr(r_col), pos_coef,
-                                           _ptr(pos_cos), _ptr(h1), _ptr(h2), dt, _ptr(inv_norm),
+            _lib.check(lib.maai_ntxent_bwd(_ptr(z_all), _ptr(r_row), _ptr(r_col), 1 if full else 0,
+                                           _ptr(rowsum), _ptr(pos_cos), _ptr(h1), _ptr(h2), dt, _ptr(inv_norm),
                                            _ptr(g), b, world, rank, d, dp, inv_tau, need, _ptr(dh1),
                                            _ptr(dh2), _ptr(dz_acc), _stream()),
                        "maai_ntxent_bwd")

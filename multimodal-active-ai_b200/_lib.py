@@ -24,7 +24,7 @@ SIGNATURES = {
                                        _c_void_p, _c_void_p, _c_void_p]),
     "maai_ntxent_fwd": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p,
                                  _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
-    "maai_ntxent_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_float, _c_void_p, _c_void_p, _c_void_p,
+    "maai_ntxent_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                  _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
                                  _c_float, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "maai_launch_count": (ctypes.c_ulonglong, []),

@@ -215,7 +215,7 @@ int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, f
   MAAI_CUDA(cudaMemsetAsync(rowsum_l, 0, sizeof(float) * m_loc, s));
   const char* q_base = static_cast<const char*>(z_glob) + (size_t)rank * m_loc * d_pad * 2;
   rc = dispatch_tile<false>(d_pad, q_base, m_loc, z_glob, m_glob, rank * m_loc, inv_tau, nullptr,
-                            nullptr, rowsum_l, nullptr, 0, 0, s);
+                            nullptr, rowsum_l, nullptr, b, b, s);
   if (rc != MAAI_OK) return rc;
   maai::finalize_loss_kernel<<<1, 1024, 0, s>>>(rowsum_l, pos_cos, b, inv_tau, r_out, loss_out);
   ++g_launches;
@@ -223,11 +223,11 @@ int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, f
   return MAAI_OK;
 }
 
-int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, float pos_coef,
-                    const float* pos_cos, const void* h1, const void* h2, int in_dtype,
+int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, int key_grad,
+                    const float* rowsum_l, const float* pos_cos, const void* h1, const void* h2, int in_dtype,
                     const float* inv_norm, const float* grad_loss, int b, int world, int rank, int d, int d_pad,
                     float inv_tau, int need_mask, void* dh1, void* dh2, float* dz_acc, void* stream) {
-  if (!z_glob || !r_row || !r_col || !pos_cos || !h1 || !h2 || !inv_norm || !grad_loss || !dz_acc)
+  if (!z_glob || !r_row || !r_col || !rowsum_l || !pos_cos || !h1 || !h2 || !inv_norm || !grad_loss || !dz_acc)
     return fail(MAAI_E_ARG, "null pointer");
   int rc = check_common(b, world, rank);
   if (rc != MAAI_OK) return rc;
@@ -254,20 +254,19 @@ int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, 
   switch (in_dtype) {
     case MAAI_DT_F32:
       maai::dh_kernel<float><<<grid, wpb * 32, 0, s>>>(
-          dz_acc, static_cast<const float*>(h1), static_cast<const float*>(h2), inv_norm, grad_loss, r_row,
-          r_col + (size_t)rank * m_loc, pos_cos, b, d, d_pad, inv_tau, pos_coef, need_mask, static_cast<float*>(dh1), static_cast<float*>(dh2));
+          dz_acc, static_cast<const float*>(h1), static_cast<const float*>(h2), inv_norm, grad_loss, rowsum_l,
+          pos_cos, b, d, d_pad, inv_tau, key_grad, need_mask, static_cast<float*>(dh1), static_cast<float*>(dh2));
       break;
     case MAAI_DT_BF16:
       maai::dh_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, s>>>(
           dz_acc, static_cast<const __nv_bfloat16*>(h1), static_cast<const __nv_bfloat16*>(h2),
-          inv_norm, grad_loss, r_row, r_col + (size_t)rank * m_loc, pos_cos, b, d, d_pad, inv_tau,
-          pos_coef, need_mask, static_cast<__nv_bfloat16*>(dh1),
+          inv_norm, grad_loss, rowsum_l, pos_cos, b, d, d_pad, inv_tau, key_grad, need_mask, static_cast<__nv_bfloat16*>(dh1),
           static_cast<__nv_bfloat16*>(dh2));
       break;
     case MAAI_DT_F16:
       maai::dh_kernel<__half><<<grid, wpb * 32, 0, s>>>(
           dz_acc, static_cast<const __half*>(h1), static_cast<const __half*>(h2), inv_norm, grad_loss,
-          r_row, r_col + (size_t)rank * m_loc, pos_cos, b, d, d_pad, inv_tau, pos_coef, need_mask,
+          rowsum_l, pos_cos, b, d, d_pad, inv_tau, key_grad, need_mask,
           static_cast<__half*>(dh1), static_cast<__half*>(dh2));
       break;
     default:

@@ -73,20 +73,22 @@ normalize_cast_kernel(const T* __restrict__ h1, const T* __restrict__ h2, int b,
   }
 }
 
-// Single block, deterministic: loss = (1/b) * sum_{i < 2b} [ ln(l_i) + (1 - cos_pos(i)) / tau ]
-// (lse_i = 1/tau + ln l_i because E was taken relative to the fixed maximum 1/tau) and
-// r_i = 1 / (b * l_i) for the backward.  r_out may be null.
+// Single block, deterministic.  With e_pos = exp((cos_pos - 1)/tau) and l' = sum over negatives:
+//   lse_i - s_i,pos = ln(e_pos + l'_i) - ln(e_pos) = log1p(l'_i / e_pos)      (Objective.py:76-77)
+//   loss = (1/b) * sum_{i < 2b} log1p(l'_i / e_pos(i))                          (Objective.py:79)
+// and r_i = 1 / (b * (e_pos + l'_i)) for the backward.  r_out may be null.
 __global__ void __launch_bounds__(1024)
 finalize_loss_kernel(const float* __restrict__ l, const float* __restrict__ pos_cos, int b,
                      float inv_tau, float* __restrict__ r_out, float* __restrict__ loss_out) {
   __shared__ double part[32];
   double acc = 0.0;
   const float inv_b = 1.f / float(b);
+  const float c1 = inv_tau * 1.4426950408889634f;
   for (int i = threadIdx.x; i < 2 * b; i += blockDim.x) {
-    const float li = l[i];
-    const float cp = pos_cos[i < b ? i : i - b];
-    acc += double(logf(li) + (1.f - cp) * inv_tau);
-    if (r_out) r_out[i] = inv_b / li;
+    const float ln = l[i];
+    const float ep = ex2_approx(fmaf(pos_cos[i < b ? i : i - b], c1, -c1));
+    acc += double(log1pf(ln / ep));
+    if (r_out) r_out[i] = inv_b / (ep + ln);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -101,19 +103,18 @@ finalize_loss_kernel(const float* __restrict__ l, const float* __restrict__ pos_
 }
 
 // One warp per anchor row i of the views that need a gradient.
-//   dz_i = (g / tau) * (A_i + [E_i,pos (rr_i + rc_pos) - pos_coef] z_pos(i)),  A = dz_acc (fp32,
-//          stride dp, positive column excluded), pos_coef = 2/b (full gradient) or 1/b (query side
-//          only).  The bracket is the positive pair's softmax-minus-target coefficient, evaluated
-//          in fp32 from the same bf16 cosine the forward used.
+//   dz_i = (g / tau) * (A_i + cpos_i z_pos(i)),  A = dz_acc (fp32, stride dp, positive column excluded)
+//   cpos_i = [e_pos/(e_pos + l'_i) - 1]/b  (+ the same with l'_pos when the key side is kept)
+//          = -(1/b) [ l'_i/(e_pos + l'_i) + key_grad * l'_pos/(e_pos + l'_pos) ]
+// i.e. the positive pair's softmax-minus-target coefficient without any cancellation.
 //   dh_i = inv_i * (dz_i - z_i (z_i . dz_i))       (rows with ||h|| < eps: dh = dz * inv)
 // z_i, z_pos are recomputed in fp32 from h (not the bf16 copies).
 template <typename T>
 __global__ void __launch_bounds__(256)
 dh_kernel(const float* __restrict__ dz_acc, const T* __restrict__ h1, const T* __restrict__ h2,
           const float* __restrict__ inv_norm, const float* __restrict__ grad_loss,
-          const float* __restrict__ r_row, const float* __restrict__ r_col_loc,
-          const float* __restrict__ pos_cos, int b, int d, int dp, float inv_tau, float pos_coef,
-          int need_mask, T* __restrict__ dh1, T* __restrict__ dh2) {
+          const float* __restrict__ lneg, const float* __restrict__ pos_cos, int b, int d, int dp,
+          float inv_tau, int key_grad, int need_mask, T* __restrict__ dh1, T* __restrict__ dh2) {
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   // rows are enumerated over the views that need a gradient
@@ -131,7 +132,8 @@ dh_kernel(const float* __restrict__ dz_acc, const T* __restrict__ h1, const T* _
   const int ip = view ? k : b + k;  // local row of the positive
   const float c1 = inv_tau * 1.4426950408889634f;
   const float e_pos = ex2_approx(fmaf(pos_cos[k], c1, -c1));
-  const float cpos = e_pos * (r_row[i] + r_col_loc[ip]) - pos_coef;
+  const float li = lneg[i], lp = lneg[ip];
+  const float cpos = -(li / (e_pos + li) + (key_grad ? lp / (e_pos + lp) : 0.f)) / float(b);
   float z[kMaxPerLane], dz[kMaxPerLane];
   float dot = 0.f;
 #pragma unroll

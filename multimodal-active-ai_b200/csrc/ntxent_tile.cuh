@@ -7,13 +7,14 @@
 // Formulation.  Z = all normalised rows (bf16), M_glob = 2B of them,
 // this rank owns M_loc = 2b "anchor" rows.  With c1 = log2(e)/tau and the fixed maximum 1/tau
 // (rows are unit-norm, so every logit is <= 1/tau):
-//     E_ij = exp2(c1 * z_i.z_j - c1)         (j != i, j < M_glob)
-//   FWD:  l_i  = sum_j E_ij                                     -> atomically added to l[]
-//   BWD:  A_i  = sum_{j != pos(i)} E_ij (rr_i + rc_j) z_j       -> atomically added to dz_acc[]
+//     E_ij = exp2(c1 * z_i.z_j - c1)         (j != i, j != pos(i), j < M_glob)
+//   FWD:  l'_i = sum_j E_ij   (negatives only)                  -> atomically added to l[]
+//   BWD:  A_i  = sum_j E_ij (rr_i + rc_j) z_j                   -> atomically added to dz_acc[]
 //         (full gradient: rr = rc = r = 1/(b*l); query-side only: rc = 0; key-side only: rr = 0).
-//         The positive column is left out of the bf16 MMA on purpose: its coefficient
-//         E_i,pos (rr_i + rc_pos) - 2/b cancels to a small residual when the softmax is peaked, so
-//         dh_kernel adds it in fp32.
+//   The positive column is left out of both on purpose.  When the softmax is peaked the positive
+//   dominates the row sum and its gradient coefficient E_i,pos (rr_i + rc_pos) - 2/b cancels to a
+//   small residual; folding it in fp32 afterwards (finalize_loss_kernel: log1p(l'/e_pos),
+//   dh_kernel: -(1/b) l'/(e_pos + l')) keeps loss and gradient exact at small temperatures.
 // (the positive-pair term and the normalisation Jacobian are O(M d) and live in ntxent_aux.cuh).
 //
 // One persistent CTA per SM walks a contiguous range of (row block, key tile) items
@@ -35,7 +36,7 @@ struct TileParams {
   int m_loc;             // anchor rows covered by tmap_q
   int m_glob;            // key rows covered by tmap_k
   int row_global_base;   // global (key-space) index of anchor row 0
-  int pos_split;         // BWD: anchor rows < pos_split have their positive at +pos_delta, others at -pos_delta
+  int pos_split;         // anchor rows < pos_split have their positive at +pos_delta, others at -pos_delta
   int pos_delta;         //      (= b; pos_split = b - first anchor row of this launch)
   int nrb;               // row blocks
   int nkt;               // key tiles (128 keys each)
@@ -297,8 +298,8 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const bool valid = row < p.m_loc;
       const int grow = p.row_global_base + row;                 // same row in key space
       const int g0 = p.row_global_base + rb * C::RB_ROWS + q * 128;
-      // BWD: key index of this row's positive (masked like the diagonal); FWD: never matches
-      const int gpos = BWD ? (row < p.pos_split ? grow + p.pos_delta : grow - p.pos_delta) : -1;
+      // key index of this row's positive (masked like the diagonal)
+      const int gpos = row < p.pos_split ? grow + p.pos_delta : grow - p.pos_delta;
       float r_i = 0.f;
       if (BWD && valid) r_i = __ldg(p.r_row + row);
       float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
@@ -310,11 +311,10 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const int st = tk % NST;
         const int ub = uu % SBUF;
         const int k0 = (j0 + jj) * C::KT;
-        // tiles that hold a diagonal entry, a positive (BWD; a Q tile may straddle the view
+        // tiles that hold a diagonal entry, a positive (a Q tile may straddle the view
         // boundary, so test both placements) or keys past the end need per-element predicates
         bool special = (k0 < g0 + 128 && g0 < k0 + C::KT) || (k0 + C::KT > p.m_glob);
-        if (BWD)
-          special = special || (k0 < g0 - p.pos_delta + 128 && g0 - p.pos_delta < k0 + C::KT) ||
+        special = special || (k0 < g0 - p.pos_delta + 128 && g0 - p.pos_delta < k0 + C::KT) ||
                     (k0 < g0 + p.pos_delta + 128 && g0 + p.pos_delta < k0 + C::KT);
         if (BWD) mbar_wait(bar_k_full(st), (tk / NST) & 1);  // r_j of this stage has landed
         mbar_wait(bar_s_full(slot, ub), (uu / SBUF) & 1);

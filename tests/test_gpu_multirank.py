@@ -1,0 +1,82 @@
+"""Multi-rank parity on the GPU.
+
+* ``test_emulated_ranks_one_gpu``: every rank's K1 -> (gather = the shared buffer) -> K2 -> K3/K4
+  is driven through the C ABI on ONE GPU, rank after rank, and compared with the fp64 oracle of the
+  reference's world_size>1 branch: per-rank loss (Objective.py:51-79), the reference's query-side-
+  only gradient (key_grad=0) and the full gradient (key_grad=1).
+* ``test_two_gpu_torchrun``: the public API under torch.distributed.run with 2 real ranks (NCCL);
+  skipped when fewer than 2 GPUs are visible.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, rel_fro
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("world,b,d,tau", [(2, 96, 128, 0.5), (4, 200, 64, 0.1), (8, 64, 128, 0.5), (3, 130, 256, 0.2)])
+def test_emulated_ranks_one_gpu(world, b, d, tau):
+    import maai_b200
+    from maai_b200 import _lib
+    from oracle import ntxent_oracle as O
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(world * 1000 + b)
+    H1 = torch.randn(world * b, d, generator=g)
+    H2 = H1 + 0.5 * torch.randn(world * b, d, generator=g)
+    h1r = [H1[p * b:(p + 1) * b].contiguous() for p in range(world)]
+    h2r = [H2[p * b:(p + 1) * b].contiguous() for p in range(world)]
+    dp = lib.maai_padded_dim(d)
+    z_all = torch.zeros(world, 2 * b, dp, dtype=torch.bfloat16, device=dev)
+    inv = torch.zeros(world, 2 * b, device=dev)
+    cos = torch.zeros(world, b, device=dev)
+    dh = [(h1r[p].to(dev), h2r[p].to(dev)) for p in range(world)]
+    for p in range(world):
+        _lib.check(lib.maai_ntxent_normalize(dh[p][0].data_ptr(), dh[p][1].data_ptr(), b, d, 0,
+                                             z_all[p].data_ptr(), inv[p].data_ptr(), cos[p].data_ptr(), s), "k1")
+    rowsum = torch.zeros(world, 2 * b, device=dev)
+    r_col = torch.zeros(lib.maai_ntxent_r_len(b, world), device=dev)
+    losses = torch.zeros(world, device=dev)
+    for p in range(world):
+        _lib.check(lib.maai_ntxent_fwd(z_all.data_ptr(), b, world, p, dp, 1.0 / tau, cos[p].data_ptr(),
+                                       rowsum[p].data_ptr(), r_col[p * 2 * b:].data_ptr(),
+                                       losses[p:].data_ptr(), s), "k2")
+    ol, o1q, o2q = O.contrastive_loss_oracle_distributed([h.numpy() for h in h1r], [h.numpy() for h in h2r], tau, key_grad=False)
+    _, o1f, o2f = O.contrastive_loss_oracle_distributed([h.numpy() for h in h1r], [h.numpy() for h in h2r], tau, key_grad=True)
+    got = losses.cpu().numpy()
+    for p in range(world):
+        assert abs(got[p] - ol[p]) <= 1e-3 * abs(ol[p])
+    one = torch.ones((), device=dev)
+    zeros = torch.zeros_like(r_col)
+    acc = torch.empty(2 * b, dp, device=dev)
+    for p in range(world):
+        r_row = r_col[p * 2 * b:(p + 1) * 2 * b].clone()
+        for key_grad, (r1, r2) in ((1, (o1f, o2f)), (0, (o1q, o2q))):
+            g1 = torch.zeros(b, d, device=dev); g2 = torch.zeros(b, d, device=dev)
+            _lib.check(lib.maai_ntxent_bwd(z_all.data_ptr(), r_row.data_ptr(),
+                                           (r_col if key_grad else zeros).data_ptr(), key_grad,
+                                           rowsum[p].data_ptr(), cos[p].data_ptr(), dh[p][0].data_ptr(),
+                                           dh[p][1].data_ptr(), 0, inv[p].data_ptr(), one.data_ptr(), b, world, p,
+                                           d, dp, 1.0 / tau, 3, g1.data_ptr(), g2.data_ptr(), acc.data_ptr(), s), "k3")
+            torch.cuda.synchronize()
+            assert rel_fro(g1.cpu().numpy(), r1[p]) <= 1e-2, (p, key_grad)
+            assert rel_fro(g2.cpu().numpy(), r2[p]) <= 1e-2, (p, key_grad)
+
+
+def test_two_gpu_torchrun(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    out = tmp_path / "dist.npz"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29655",
+           os.path.join(ROOT, "tests", "_dist_gpu_worker.py"), str(out)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "DIST_OK" in res.stdout
