@@ -23,8 +23,11 @@
 //   warp 1 lane 0 : tcgen05.mma issuer (S = Q K^T into TMEM; BWD also A += P Z_J with P read
 //                   from TMEM and Z_J read from the *same* smem tile as an MN-major operand)
 //   warp 2        : TMEM allocator
-//   warps 4-7 / 8-11 : two "slots" of 128 threads, one TMEM lane (= one anchor row) per thread:
-//                   tcgen05.ld S -> exp2 -> row sum (FWD) / P = E (r_i + r_j) -> bf16 -> TMEM (BWD)
+//   warps 4-11 / 12-19 : two "slots" of 256 threads.  A slot owns one S tile at a time; its two
+//                   warpgroups split the 128 key columns (64 each), one TMEM lane (= anchor row)
+//                   per thread: tcgen05.ld S -> exp2 -> row sum (FWD) / P = E (r_i + r_j) -> bf16
+//                   -> TMEM (BWD).  Four softmax warps per SM sub-partition hide tcgen05.ld / MUFU
+//                   latency (ncu of the 1-warpgroup-per-slot version: profiles/r1_ncu_summary_v1.md).
 // D <= 128: a row block is two 128-row Q tiles, slot s owns Q tile s (each K tile feeds both).
 // D == 256: a row block is one Q tile, the slots take alternate key tiles.
 #pragma once
@@ -62,7 +65,7 @@ struct TileCfg {
   static constexpr int SBUF = BWD ? 1 : 2;             // S buffers per slot
   static constexpr int TMEM_S0 = 0;                    // S buffers: slot s, buffer u -> (s*SBUF+u)*128
   static constexpr int TMEM_DZ0 = 256;                 // BWD accumulators: 256 + q*D
-  static constexpr int NTHREADS = 384;
+  static constexpr int NTHREADS = 640;
   // shared memory carve-up (offsets from a 1024-B aligned base)
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + NQ * TILE_BYTES;
@@ -74,7 +77,7 @@ struct TileCfg {
 };
 
 template <int D, bool BWD>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(640, 1)
 ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
                    const __grid_constant__ CUtensorMap tmap_k, const TileParams p) {
   using C = TileCfg<D, BWD>;
@@ -120,10 +123,10 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
     for (int s = 0; s < 2; ++s)
       for (int u = 0; u < SBUF; ++u) {
         mbar_init(bar_s_full(s, u), 1);
-        mbar_init(bar_sm_done(s, u), 128);
+        mbar_init(bar_sm_done(s, u), 256);
       }
     mbar_init(bar_dz_full, 1);
-    mbar_init(bar_dz_free, 256);
+    mbar_init(bar_dz_free, 512);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -173,118 +176,137 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
     __syncwarp();
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128, 0);
-      constexpr uint32_t IDESC_PV = make_idesc_bf16(128, D, 1);
-      uint32_t t = 0;         // key tiles consumed so far (ring position)
-      uint32_t useg = 0;
-      uint32_t u[2] = {0, 0};  // S tiles issued per slot
-      uint32_t sig = 0;        // S tiles issued in total (NQ == 1: slot = sig & 1)
+    // The whole warp walks the schedule (warp-uniform control flow and descriptor arithmetic);
+    // one elected lane executes each tcgen05.mma / tcgen05.commit.
+    constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128, 0);
+    constexpr uint32_t IDESC_PV = make_idesc_bf16(128, D, 1);
+    // descriptor of tile base address 0; real addresses are added to the low word (>> 4)
+    const uint64_t sdesc_k = make_sdesc_sw128(0, 16, 1024);             // K-major: SBO = 8 rows
+    const uint64_t sdesc_mn = make_sdesc_sw128(0, p.pv_lbo, p.pv_sbo);  // MN-major Z_J for P.Z
+    uint32_t t = 0;          // key tiles consumed so far (ring position)
+    uint32_t useg = 0;
+    uint32_t u0 = 0, u1 = 0;  // S tiles issued per slot
+    uint32_t sig = 0;         // S tiles issued in total (NQ == 1: slot = sig & 1)
 
-      // S tile: slot `slot` <- Q tile `q` x K stage `st`
-      auto issue_s = [&](int slot, int q, int st) {
-        const int ub = u[slot] % SBUF;
-        if (!BWD) {  // FWD: wait until the softmax slot has drained this buffer
-          mbar_wait(bar_sm_done(slot, ub), ((u[slot] / SBUF) & 1) ^ 1);
-          tc_fence_after();
-        }
-        const uint32_t d_tmem = tmem_base + C::TMEM_S0 + (slot * SBUF + ub) * 128;
+    // S tile: slot `slot` <- Q tile `q` x K stage `st`
+    auto issue_s = [&](int slot, int q, int st) {
+      const uint32_t us = slot ? u1 : u0;
+      const int ub = us % SBUF;
+      if (!BWD) {  // FWD: wait until the softmax slot has drained this buffer
+        mbar_wait(bar_sm_done(slot, ub), ((us / SBUF) & 1) ^ 1);
+        tc_fence_after();
+      }
+      const uint32_t d_tmem = tmem_base + C::TMEM_S0 + (slot * SBUF + ub) * 128;
+      const uint64_t ad = sdesc_k + ((sQ + q * C::TILE_BYTES) >> 4);
+      const uint64_t bd = sdesc_k + ((sK + st * C::TILE_BYTES) >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
-          const uint32_t off = (k >> 2) * C::CHUNK_BYTES + (k & 3) * 32;
-          const uint64_t ad = make_sdesc_sw128(sQ + q * C::TILE_BYTES + off, 16, 1024);
-          const uint64_t bd = make_sdesc_sw128(sK + st * C::TILE_BYTES + off, 16, 1024);
-          umma_ss(d_tmem, ad, bd, IDESC_S, k > 0);
+          const uint32_t off = ((k >> 2) * C::CHUNK_BYTES + (k & 3) * 32) >> 4;
+          umma_ss(d_tmem, ad + off, bd + off, IDESC_S, k > 0);
         }
         umma_commit(bar_s_full(slot, ub));
-        ++u[slot];
-        ++sig;
-      };
-      // BWD: A_q += P(slot) * Z_J(stage st); P was written over S by the softmax slot
-      auto issue_pv = [&](int slot, int q, int st, uint32_t uidx, bool first) {
-        mbar_wait(bar_sm_done(slot, 0), uidx & 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + C::TMEM_DZ0 + q * D;
-        const uint32_t a_tmem = tmem_base + C::TMEM_S0 + slot * 128;
+      }
+      __syncwarp();
+      if (slot) ++u1; else ++u0;
+      ++sig;
+    };
+    // BWD: A_q += P(slot) * Z_J(stage st); P was written over S by the softmax slot
+    auto issue_pv = [&](int slot, int q, int st, uint32_t uidx, bool first) {
+      mbar_wait(bar_sm_done(slot, 0), uidx & 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + C::TMEM_DZ0 + q * D;
+      const uint32_t a_tmem = tmem_base + C::TMEM_S0 + slot * 128;
+      const uint64_t bd = sdesc_mn + ((sK + st * C::TILE_BYTES) >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < C::KT / 16; ++k) {
-          // 16 keys = 16 smem rows of 128 B; MN-major: LBO = next 64-column chunk, SBO = next 8 rows
-          const uint64_t bd =
-              make_sdesc_sw128(sK + st * C::TILE_BYTES + k * 2048, p.pv_lbo, p.pv_sbo);
-          umma_ts(d_tmem, a_tmem + k * 8, bd, IDESC_PV, (first && k == 0) ? 0u : 1u);
+          // 16 keys = 16 smem rows of 128 B (2048 B); P of key half h (64 keys, 32 packed
+          // columns) sits at S columns [h*64, h*64+32)
+          umma_ts(d_tmem, a_tmem + (k >> 2) * 64 + (k & 3) * 8, bd + k * (2048 >> 4), IDESC_PV,
+                  (first && k == 0) ? 0u : 1u);
         }
-      };
-
-      for (long long it = it_begin; it < it_end;) {
-        const int j0 = int(it % p.nkt);
-        const int n = int(min((long long)(p.nkt - j0), it_end - it));
-        mbar_wait(bar_q_full, useg & 1);
-        tc_fence_after();
-        if (!BWD) {
-          for (int jj = 0; jj < n; ++jj, ++t) {
-            const int st = t % NST;
-            mbar_wait(bar_k_full(st), (t / NST) & 1);
-            tc_fence_after();
-            if (NQ == 2) {
-              issue_s(0, 0, st);
-              issue_s(1, 1, st);
-            } else {
-              issue_s(sig & 1, 0, st);
-            }
-            umma_commit(bar_k_empty(st));
-          }
-          umma_commit(bar_q_empty);
-        } else {
-          // S tiles of this segment in issue order: sigma = 0 .. ns-1;
-          // NQ == 2: sigma -> (key tile sigma >> 1, slot = Q tile = sigma & 1)
-          // NQ == 1: sigma -> (key tile sigma, slot alternates with the running count)
-          const int ns = n * NQ;
-          const uint32_t t0 = t;
-          const uint32_t slot_base = (NQ == 1) ? (sig & 1) : 0;
-          auto slot_of = [&](int sg) { return (NQ == 2) ? (sg & 1) : int((slot_base + sg) & 1); };
-          auto q_of = [&](int sg) { return (NQ == 2) ? (sg & 1) : 0; };
-          auto kt_of = [&](int sg) { return (NQ == 2) ? (sg >> 1) : sg; };
-          uint32_t upv[2] = {u[0], u[1]};  // per-slot index of the next P to consume
-          auto issue_s_sigma = [&](int sg) {
-            const uint32_t tk = t0 + kt_of(sg);
-            const int st = tk % NST;
-            if (NQ == 1 || (sg & 1) == 0) {  // first S tile that touches this key stage
-              mbar_wait(bar_k_full(st), (tk / NST) & 1);
-              tc_fence_after();
-            }
-            issue_s(slot_of(sg), q_of(sg), st);
-          };
-          issue_s_sigma(0);
-          if (ns > 1) issue_s_sigma(1);
-          if (ns <= 2) umma_commit(bar_q_empty);
-          // accumulators of the previous segment must have been flushed
-          mbar_wait(bar_dz_free, (useg & 1) ^ 1);
-          tc_fence_after();
-          for (int sg = 0; sg < ns; ++sg) {
-            const int slot = slot_of(sg), q = q_of(sg);
-            const uint32_t tk = t0 + kt_of(sg);
-            const int st = tk % NST;
-            const bool first = (NQ == 2) ? (sg < 2) : (sg == 0);
-            issue_pv(slot, q, st, upv[slot], first);
-            ++upv[slot];
-            if (NQ == 1 || (sg & 1) == 1) umma_commit(bar_k_empty(st));  // last reader of the stage
-            if (sg + 2 < ns) {
-              issue_s_sigma(sg + 2);
-              if (sg + 3 >= ns) umma_commit(bar_q_empty);  // that was the last read of the Q tiles
-            }
-          }
-          umma_commit(bar_dz_full);
-          t = t0 + n;
-        }
-        it += n;
-        ++useg;
       }
+      __syncwarp();
+    };
+    auto commit = [&](uint32_t bar) {
+      if (elect_one()) umma_commit(bar);
+      __syncwarp();
+    };
+
+#pragma unroll 1
+    for (long long it = it_begin; it < it_end;) {
+      const int j0 = int(it % p.nkt);
+      const int n = int(min((long long)(p.nkt - j0), it_end - it));
+      mbar_wait(bar_q_full, useg & 1);
+      tc_fence_after();
+      if (!BWD) {
+#pragma unroll 1
+        for (int jj = 0; jj < n; ++jj, ++t) {
+          const int st = t % NST;
+          mbar_wait(bar_k_full(st), (t / NST) & 1);
+          tc_fence_after();
+          if (NQ == 2) {
+            issue_s(0, 0, st);
+            issue_s(1, 1, st);
+          } else {
+            issue_s(sig & 1, 0, st);
+          }
+          commit(bar_k_empty(st));
+        }
+        commit(bar_q_empty);
+      } else {
+        // S tiles of this segment in issue order: sigma = 0 .. ns-1;
+        // NQ == 2: sigma -> (key tile sigma >> 1, slot = Q tile = sigma & 1)
+        // NQ == 1: sigma -> (key tile sigma, slot alternates with the running count)
+        const int ns = n * NQ;
+        const uint32_t t0 = t;
+        const uint32_t slot_base = (NQ == 1) ? (sig & 1) : 0;
+        auto slot_of = [&](int sg) { return (NQ == 2) ? (sg & 1) : int((slot_base + sg) & 1); };
+        auto q_of = [&](int sg) { return (NQ == 2) ? (sg & 1) : 0; };
+        auto kt_of = [&](int sg) { return (NQ == 2) ? (sg >> 1) : sg; };
+        uint32_t upv0 = u0, upv1 = u1;  // per-slot index of the next P to consume
+        auto issue_s_sigma = [&](int sg) {
+          const uint32_t tk = t0 + kt_of(sg);
+          const int st = tk % NST;
+          if (NQ == 1 || (sg & 1) == 0) {  // first S tile that touches this key stage
+            mbar_wait(bar_k_full(st), (tk / NST) & 1);
+            tc_fence_after();
+          }
+          issue_s(slot_of(sg), q_of(sg), st);
+        };
+        issue_s_sigma(0);
+        if (ns > 1) issue_s_sigma(1);
+        if (ns <= 2) commit(bar_q_empty);
+        // accumulators of the previous segment must have been flushed
+        mbar_wait(bar_dz_free, (useg & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int sg = 0; sg < ns; ++sg) {
+          const int slot = slot_of(sg), q = q_of(sg);
+          const uint32_t tk = t0 + kt_of(sg);
+          const int st = tk % NST;
+          const bool first = (NQ == 2) ? (sg < 2) : (sg == 0);
+          issue_pv(slot, q, st, slot ? upv1 : upv0, first);
+          if (slot) ++upv1; else ++upv0;
+          if (NQ == 1 || (sg & 1) == 1) commit(bar_k_empty(st));  // last reader of the stage
+          if (sg + 2 < ns) {
+            issue_s_sigma(sg + 2);
+            if (sg + 3 >= ns) commit(bar_q_empty);  // that was the last read of the Q tiles
+          }
+        }
+        commit(bar_dz_full);
+        t = t0 + n;
+      }
+      it += n;
+      ++useg;
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // =========================== softmax slots ===========================
-    const int slot = (warp - 4) >> 2;
-    const int w4 = warp & 3;
+    const int sw = warp - 4;
+    const int slot = sw >> 3;         // which S stream
+    const int half = (sw >> 2) & 1;   // which 64 key columns of each S tile
+    const int w4 = warp & 3;          // TMEM lane quarter this warp may touch
     const int row_in_tile = w4 * 32 + lane;
     const uint32_t lane_base = tmem_base + (uint32_t(w4 * 32) << 16);
     const float c1 = p.c1;
@@ -315,52 +337,57 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
         // boundary, so test both placements) or keys past the end need per-element predicates
         bool special = (k0 < g0 + 128 && g0 < k0 + C::KT) || (k0 + C::KT > p.m_glob);
         special = special || (k0 < g0 - p.pos_delta + 128 && g0 - p.pos_delta < k0 + C::KT) ||
-                    (k0 < g0 + p.pos_delta + 128 && g0 + p.pos_delta < k0 + C::KT);
+                  (k0 < g0 + p.pos_delta + 128 && g0 + p.pos_delta < k0 + C::KT);
         if (BWD) mbar_wait(bar_k_full(st), (tk / NST) & 1);  // r_j of this stage has landed
         mbar_wait(bar_s_full(slot, ub), (uu / SBUF) & 1);
         tc_fence_after();
-        const uint32_t s_addr = lane_base + C::TMEM_S0 + (slot * SBUF + ub) * 128;
-        const float* rk = rk_gen + st * C::KT;
+        const uint32_t s_addr = lane_base + C::TMEM_S0 + (slot * SBUF + ub) * 128 + half * 64;
+        const float* rk = rk_gen + st * C::KT + half * 64;
+        const int kbase = k0 + half * 64;
+
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
+          // single-buffered on purpose: four softmax warps per SM sub-partition cover the
+          // tcgen05.ld latency, and 64 live S registers would spill under the 640-thread cap
           uint32_t v[32];
           tmem_ld_x32(s_addr + c * 32, v);
           tc_wait_ld();
-          // pin the consumers of v[] behind the wait
 #pragma unroll
           for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));
-          float e[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            e[i] = ex2_approx(fmaf(__uint_as_float(v[i]), c1, -c1));
-          }
+          for (int i = 0; i < 32; ++i)
+            v[i] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(v[i]), c1, -c1)));
           if (special) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const int kc = k0 + c * 32 + i;
-              if (kc == grow || kc == gpos || kc >= p.m_glob) e[i] = 0.f;
+              const int kc = kbase + c * 32 + i;
+              if (kc == grow || kc == gpos || kc >= p.m_glob) v[i] = 0u;
             }
           }
           if (!BWD) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              acc0 += e[i];
-              acc1 += e[i + 1];
-              acc2 += e[i + 2];
-              acc3 += e[i + 3];
+              acc0 += __uint_as_float(v[i]);
+              acc1 += __uint_as_float(v[i + 1]);
+              acc2 += __uint_as_float(v[i + 2]);
+              acc3 += __uint_as_float(v[i + 3]);
             }
           } else {
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               const float4 rj = *reinterpret_cast<const float4*>(rk + c * 32 + i);
-              pk[i / 2] = pack_bf16x2(e[i] * (r_i + rj.x), e[i + 1] * (r_i + rj.y));
-              pk[i / 2 + 1] = pack_bf16x2(e[i + 2] * (r_i + rj.z), e[i + 3] * (r_i + rj.w));
+              pk[i / 2] = pack_bf16x2(__uint_as_float(v[i]) * (r_i + rj.x),
+                                      __uint_as_float(v[i + 1]) * (r_i + rj.y));
+              pk[i / 2 + 1] = pack_bf16x2(__uint_as_float(v[i + 2]) * (r_i + rj.z),
+                                          __uint_as_float(v[i + 3]) * (r_i + rj.w));
             }
-            // P (bf16, 2 per column) overwrites the S columns this thread has already read
+            // P (bf16, 2 keys per column) overwrites S columns this warpgroup has already read:
+            // keys [half*64 + c*32, +32) -> columns half*64 + c*16 .. +16
             tmem_st_x16(s_addr + c * 16, pk);
           }
         }
+
         if (BWD) tc_wait_st();
         tc_fence_before();
         mbar_arrive(bar_sm_done(slot, ub));
@@ -372,12 +399,11 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       } else {
         mbar_wait(bar_dz_full, useg & 1);
         tc_fence_after();
-        // NQ == 2: slot s flushes accumulator s (D columns); NQ == 1: slot s flushes columns
-        // [s*128, s*128+128) of the single 256-column accumulator
-        constexpr int NCOL = (NQ == 2) ? D : 128;
-        const uint32_t a_addr =
-            lane_base + C::TMEM_DZ0 + ((NQ == 2) ? slot * D : slot * 128);
-        const int col0 = (NQ == 2) ? 0 : slot * 128;
+        // NQ == 2: slot s owns accumulator s (D columns), its two warpgroups flush D/2 each;
+        // NQ == 1: the four warpgroups flush 64 columns each of the single 256-column accumulator
+        constexpr int NCOL = (NQ == 2) ? D / 2 : 64;
+        const int col0 = (NQ == 2) ? half * NCOL : (slot * 2 + half) * 64;
+        const uint32_t a_addr = lane_base + C::TMEM_DZ0 + ((NQ == 2) ? slot * D : 0) + col0;
 #pragma unroll
         for (int c = 0; c < NCOL / 32; ++c) {
           uint32_t v[32];

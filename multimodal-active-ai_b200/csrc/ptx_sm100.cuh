@@ -58,6 +58,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// One lane of the (fully converged) warp; the same lane every time.  The callers keep all their
+// control flow and descriptor arithmetic warp-uniform and elect only around the instruction, so the
+// compiler can leave operands in uniform registers (a `lane == 0` region forces an R2UR waterfall
+// loop of ~20 instructions in front of every UTCHMMA -- measured, profiles/r1_ncu_summary_v1.md).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------------------------
@@ -192,6 +208,14 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
       "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]),
       "r"(r[15])
       : "memory");
+}
+
+// Register re-distribution between warpgroups (all 4 warps of a warpgroup must execute it)
+template <int N> __device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N> __device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
