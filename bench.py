@@ -305,7 +305,7 @@ def main():
             "gpu_launches": int(main_r["launches"]),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["bf16"]) if achieved else None, "traffic": None,
-                         "kernel": f"ntxent_tile_kernel<{maai_b200.padded_dim(d)},BWD>",
+                         "kernel": f"ntxent_tile_kernel<D={maai_b200.padded_dim(d)},BWD,NQ=1>",
                          "how": "16*b*B*d algorithmic flops / mean CUDA-event time of the maai_ntxent_bwd call "
                                 "(memset + tile kernel + dh kernel) over the timed steps",
                          "peak_source": peaks["source"] + ", burst cuBLAS bf16",

@@ -6,7 +6,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmaai_ntxent.so")
+# MAAI_DEBUG_LIB selects an A/B build of the same library (tools/ab_variants.py); never a fallback
+LIB_PATH = os.environ.get("MAAI_DEBUG_LIB") or os.path.join(HERE, "libmaai_ntxent.so")
 
 ABI_VERSION = 1
 OK, E_ARG, E_SHAPE, E_CUDA = 0, -1, -2, -3

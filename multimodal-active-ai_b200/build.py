@@ -34,10 +34,13 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defs: tuple = (), out: str | None = None) -> str:
+    """defs/out: A/B variants for tuning (e.g. defs=("MAAI_POLY_FWD=4",), out="/tmp/x.so")."""
+    target = out or LIB
+    if not force and not out and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defs], "-o", target,
+           *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -47,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError(f"nvcc failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
     if verbose:
         print(res.stderr)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

@@ -79,15 +79,15 @@ int sm_count() {
   return n;
 }
 
-template <int D, bool BWD>
+template <int D, bool BWD, int NQ>
 int launch_tile(const void* q_base, int m_loc, const void* k_base, int m_glob, int row_global_base,
                 float inv_tau, const float* r_row, const float* r_col, float* l_out, float* dz_acc,
                 int pos_split, int pos_delta, cudaStream_t s) {
-  using C = maai::TileCfg<D, BWD>;
+  using C = maai::TileCfg<D, BWD, NQ>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(maai::ntxent_tile_kernel<D, BWD>,
+    attr_err = cudaFuncSetAttribute(maai::ntxent_tile_kernel<D, BWD, NQ>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(smem)", attr_err);
@@ -117,29 +117,41 @@ int launch_tile(const void* q_base, int m_loc, const void* k_base, int m_glob, i
   int sms = sm_count();
   if (sms <= 0) return fail(MAAI_E_CUDA, "no CUDA device");
   const int grid = (int)(items < sms ? items : sms);
-  maai::ntxent_tile_kernel<D, BWD><<<grid, C::NTHREADS, C::SMEM_BYTES, s>>>(tq, tk, p);
+  maai::ntxent_tile_kernel<D, BWD, NQ><<<grid, C::NTHREADS, C::SMEM_BYTES, s>>>(tq, tk, p);
   ++g_launches;
   MAAI_CUDA(cudaGetLastError());
   return MAAI_OK;
+}
+
+// Q tiles per row block.  Forward (MUFU-bound): two, to halve the L2 -> smem traffic per flop.
+// Backward: one, which leaves TMEM room for three S buffers (see ntxent_tile.cuh).
+// MAAI_DEBUG_BWD_NQ=2 / MAAI_DEBUG_FWD_NQ=1 select the other layout for A/B measurements.
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
 }
 
 template <bool BWD>
 int dispatch_tile(int d_pad, const void* q_base, int m_loc, const void* k_base, int m_glob,
                   int row_global_base, float inv_tau, const float* r_row, const float* r_col,
                   float* l_out, float* dz_acc, int pos_split, int pos_delta, cudaStream_t s) {
+  static const int nq = BWD ? env_int("MAAI_DEBUG_BWD_NQ", 1) : env_int("MAAI_DEBUG_FWD_NQ", 2);
+#define MAAI_LAUNCH(DD, NQQ)                                                                       \
+  return launch_tile<DD, BWD, NQQ>(q_base, m_loc, k_base, m_glob, row_global_base, inv_tau, r_row, \
+                                   r_col, l_out, dz_acc, pos_split, pos_delta, s)
   switch (d_pad) {
     case 64:
-      return launch_tile<64, BWD>(q_base, m_loc, k_base, m_glob, row_global_base, inv_tau, r_row,
-                                  r_col, l_out, dz_acc, pos_split, pos_delta, s);
+      if (nq == 2) MAAI_LAUNCH(64, 2);
+      MAAI_LAUNCH(64, 1);
     case 128:
-      return launch_tile<128, BWD>(q_base, m_loc, k_base, m_glob, row_global_base, inv_tau, r_row,
-                                   r_col, l_out, dz_acc, pos_split, pos_delta, s);
+      if (nq == 2) MAAI_LAUNCH(128, 2);
+      MAAI_LAUNCH(128, 1);
     case 256:
-      return launch_tile<256, BWD>(q_base, m_loc, k_base, m_glob, row_global_base, inv_tau, r_row,
-                                   r_col, l_out, dz_acc, pos_split, pos_delta, s);
+      MAAI_LAUNCH(256, 1);
     default:
       return fail(MAAI_E_SHAPE, "d_pad must be 64, 128 or 256");
   }
+#undef MAAI_LAUNCH
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

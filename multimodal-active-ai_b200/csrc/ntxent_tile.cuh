@@ -18,20 +18,35 @@
 // (the positive-pair term and the normalisation Jacobian are O(M d) and live in ntxent_aux.cuh).
 //
 // One persistent CTA per SM walks a contiguous range of (row block, key tile) items
-// ("stream-K"); a maximal run of items inside one row block is a segment.  Roles:
+// ("stream-K"); a maximal run of items inside one row block is a segment.  Every item yields NQ
+// "S tiles" (128 anchors x 128 keys); the CTA-wide running S-tile index sigma fixes, identically in
+// every role, which softmax team (sigma & 1) and which TMEM buffer a tile uses.  Roles:
 //   warp 0 lane 0 : TMA producer   (Q tiles once per segment, K tiles + r_j through a ring)
-//   warp 1 lane 0 : tcgen05.mma issuer (S = Q K^T into TMEM; BWD also A += P Z_J with P read
-//                   from TMEM and Z_J read from the *same* smem tile as an MN-major operand)
+//   warp 1        : tcgen05.mma issuer, warp-uniform control flow, one elected lane per instruction
+//                   (S = Q K^T into TMEM; BWD also A += P Z_J with P read from TMEM and Z_J read
+//                   from the *same* smem tile as an MN-major operand)
 //   warp 2        : TMEM allocator
-//   warps 4-11 / 12-19 : two "slots" of 256 threads.  A slot owns one S tile at a time; its two
-//                   warpgroups split the 128 key columns (64 each), one TMEM lane (= anchor row)
-//                   per thread: tcgen05.ld S -> exp2 -> row sum (FWD) / P = E (r_i + r_j) -> bf16
-//                   -> TMEM (BWD).  Four softmax warps per SM sub-partition hide tcgen05.ld / MUFU
-//                   latency (ncu of the 1-warpgroup-per-slot version: profiles/r1_ncu_summary_v1.md).
-// D <= 128: a row block is two 128-row Q tiles, slot s owns Q tile s (each K tile feeds both).
-// D == 256: a row block is one Q tile, the slots take alternate key tiles.
+//   warps 4-11 / 12-19 : two softmax "teams" of 256 threads.  A team owns one S tile at a time; its
+//                   two warpgroups split the 128 key columns (64 each), one TMEM lane (= anchor
+//                   row) per thread: tcgen05.ld S -> exp2 -> row sum (FWD) / P = E (r_i + r_j) ->
+//                   bf16 -> TMEM over the S columns already consumed (BWD).
+// NQ == 2 (two 128-row Q tiles per row block, team t owns Q tile t, each K tile feeds both): halves
+//   the L2 -> smem traffic per flop; used by the MUFU-bound forward.
+// NQ == 1 (one Q tile, teams take alternate key tiles): leaves TMEM room for three S buffers next
+//   to the accumulator, so the tensor pipe always has another tile's MMAs to run while a softmax
+//   is in flight; used by the backward (profiles/r1_ncu_summary_v1.md shows the exposed
+//   S -> softmax -> P -> PV chain of the one-buffer-per-Q-tile layout).
 #pragma once
 #include "ptx_sm100.cuh"
+
+// Of every 8 column pairs a softmax thread handles, this many take the polynomial exp2 on the FMA
+// pipe instead of MUFU.EX2 (build-time knobs so the split can be A/B-measured).
+#ifndef MAAI_POLY_FWD
+#define MAAI_POLY_FWD 3
+#endif
+#ifndef MAAI_POLY_BWD
+#define MAAI_POLY_BWD 0
+#endif
 
 namespace maai {
 
@@ -52,36 +67,51 @@ struct TileParams {
   uint32_t pv_sbo;
 };
 
-template <int D, bool BWD>
+template <int D, bool BWD, int NQ>
 struct TileCfg {
   static_assert(D == 64 || D == 128 || D == 256, "padded embedding dim must be 64, 128 or 256");
-  static constexpr int NQ = (D <= 128) ? 2 : 1;        // Q tiles per row block
+  static_assert(NQ == 1 || NQ == 2, "one or two Q tiles per row block");
+  static_assert(NQ == 1 || D <= 128, "two Q tiles need D <= 128 (smem, TMEM)");
   static constexpr int RB_ROWS = 128 * NQ;
   static constexpr int KT = 128;                       // keys per tile
   static constexpr int CHUNKS = D / 64;                // 128-byte swizzle chunks per row
   static constexpr int CHUNK_BYTES = 128 * 128;        // 128 rows x 128 B
   static constexpr int TILE_BYTES = CHUNKS * CHUNK_BYTES;
   static constexpr int NST = (D == 256) ? 2 : 4;       // K ring depth
-  static constexpr int SBUF = BWD ? 1 : 2;             // S buffers per slot
-  static constexpr int TMEM_S0 = 0;                    // S buffers: slot s, buffer u -> (s*SBUF+u)*128
-  static constexpr int TMEM_DZ0 = 256;                 // BWD accumulators: 256 + q*D
+  // S buffers (128 TMEM columns each).  FWD: all of TMEM.  BWD: what the accumulators leave.
+  static constexpr int NB = !BWD ? 4 : (NQ == 2 ? 2 : (D <= 128 ? 3 : 2));
+  static constexpr int TMEM_DZ0 = NB * 128;            // BWD accumulators: DZ0 + q*D
+  static_assert(!BWD || NB * 128 + NQ * D <= 512, "TMEM budget");
   static constexpr int NTHREADS = 640;
   // shared memory carve-up (offsets from a 1024-B aligned base)
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + NQ * TILE_BYTES;
   static constexpr int OFF_RK = OFF_K + NST * TILE_BYTES;
   static constexpr int OFF_BAR = OFF_RK + NST * KT * 4;
-  static constexpr int NBAR = 2 + 2 * NST + 2 * 2 * SBUF + 2;
+  static constexpr int NBAR = 2 + 2 * NST + 2 * NB + 2;
   static constexpr int OFF_TMEMPTR = OFF_BAR + NBAR * 8;
   static constexpr int SMEM_BYTES = OFF_TMEMPTR + 16 + 1024;  // + alignment slack
 };
 
-template <int D, bool BWD>
+// TMEM buffer and mbarrier phase of the S tile with CTA-wide running index `sg`.
+template <int NQ, int NB>
+__device__ __forceinline__ void s_tile_slot(uint32_t sg, int& buf, uint32_t& phase) {
+  if (NQ == 2) {  // team = sg & 1 owns buffers [team*NB/2, (team+1)*NB/2)
+    const uint32_t team = sg & 1, u = sg >> 1;
+    buf = int(team * (NB / 2) + u % (NB / 2));
+    phase = (u / (NB / 2)) & 1;
+  } else {
+    buf = int(sg % NB);
+    phase = (sg / NB) & 1;
+  }
+}
+
+template <int D, bool BWD, int NQ>
 __global__ void __launch_bounds__(640, 1)
 ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
                    const __grid_constant__ CUtensorMap tmap_k, const TileParams p) {
-  using C = TileCfg<D, BWD>;
-  constexpr int NQ = C::NQ, NST = C::NST, SBUF = C::SBUF;
+  using C = TileCfg<D, BWD, NQ>;
+  constexpr int NST = C::NST, NB = C::NB;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -97,12 +127,10 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
   const uint32_t bar_q_empty = bar0 + 1 * 8;
   auto bar_k_full = [&](int st) { return bar0 + (2 + st) * 8; };
   auto bar_k_empty = [&](int st) { return bar0 + (2 + NST + st) * 8; };
-  auto bar_s_full = [&](int slot, int u) { return bar0 + (2 + 2 * NST + slot * SBUF + u) * 8; };
-  auto bar_sm_done = [&](int slot, int u) {
-    return bar0 + (2 + 2 * NST + 2 * SBUF + slot * SBUF + u) * 8;
-  };
-  const uint32_t bar_dz_full = bar0 + (2 + 2 * NST + 4 * SBUF) * 8;
-  const uint32_t bar_dz_free = bar0 + (2 + 2 * NST + 4 * SBUF + 1) * 8;
+  auto bar_s_full = [&](int buf) { return bar0 + (2 + 2 * NST + buf) * 8; };
+  auto bar_sm_done = [&](int buf) { return bar0 + (2 + 2 * NST + NB + buf) * 8; };
+  const uint32_t bar_dz_full = bar0 + (2 + 2 * NST + 2 * NB) * 8;
+  const uint32_t bar_dz_free = bar0 + (2 + 2 * NST + 2 * NB + 1) * 8;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + C::OFF_TMEMPTR);
 
   const int warp = threadIdx.x >> 5;
@@ -120,13 +148,12 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       mbar_init(bar_k_full(s), 1);
       mbar_init(bar_k_empty(s), 1);
     }
-    for (int s = 0; s < 2; ++s)
-      for (int u = 0; u < SBUF; ++u) {
-        mbar_init(bar_s_full(s, u), 1);
-        mbar_init(bar_sm_done(s, u), 256);
-      }
+    for (int u = 0; u < NB; ++u) {
+      mbar_init(bar_s_full(u), 1);
+      mbar_init(bar_sm_done(u), 8);  // one arrive per warp of the team (8 warps)
+    }
     mbar_init(bar_dz_full, 1);
-    mbar_init(bar_dz_free, 512);
+    mbar_init(bar_dz_free, 16);      // one arrive per softmax warp
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -183,20 +210,23 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // descriptor of tile base address 0; real addresses are added to the low word (>> 4)
     const uint64_t sdesc_k = make_sdesc_sw128(0, 16, 1024);             // K-major: SBO = 8 rows
     const uint64_t sdesc_mn = make_sdesc_sw128(0, p.pv_lbo, p.pv_sbo);  // MN-major Z_J for P.Z
-    uint32_t t = 0;          // key tiles consumed so far (ring position)
+    uint32_t t = 0;     // key tiles consumed so far (K ring position); S-tile index = t*NQ + q
     uint32_t useg = 0;
-    uint32_t u0 = 0, u1 = 0;  // S tiles issued per slot
-    uint32_t sig = 0;         // S tiles issued in total (NQ == 1: slot = sig & 1)
 
-    // S tile: slot `slot` <- Q tile `q` x K stage `st`
-    auto issue_s = [&](int slot, int q, int st) {
-      const uint32_t us = slot ? u1 : u0;
-      const int ub = us % SBUF;
-      if (!BWD) {  // FWD: wait until the softmax slot has drained this buffer
-        mbar_wait(bar_sm_done(slot, ub), ((us / SBUF) & 1) ^ 1);
+    auto commit = [&](uint32_t bar) {
+      if (elect_one()) umma_commit(bar);
+      __syncwarp();
+    };
+    // S tile with running index sg: Q tile q x K stage st -> its TMEM buffer
+    auto issue_s = [&](uint32_t sg, int q, int st) {
+      int buf;
+      uint32_t ph;
+      s_tile_slot<NQ, NB>(sg, buf, ph);
+      if (!BWD) {  // FWD: wait until the softmax team has drained this buffer's previous tile
+        mbar_wait(bar_sm_done(buf), ph ^ 1);
         tc_fence_after();
       }
-      const uint32_t d_tmem = tmem_base + C::TMEM_S0 + (slot * SBUF + ub) * 128;
+      const uint32_t d_tmem = tmem_base + buf * 128;
       const uint64_t ad = sdesc_k + ((sQ + q * C::TILE_BYTES) >> 4);
       const uint64_t bd = sdesc_k + ((sK + st * C::TILE_BYTES) >> 4);
       if (elect_one()) {
@@ -205,18 +235,19 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
           const uint32_t off = ((k >> 2) * C::CHUNK_BYTES + (k & 3) * 32) >> 4;
           umma_ss(d_tmem, ad + off, bd + off, IDESC_S, k > 0);
         }
-        umma_commit(bar_s_full(slot, ub));
+        umma_commit(bar_s_full(buf));
       }
       __syncwarp();
-      if (slot) ++u1; else ++u0;
-      ++sig;
     };
-    // BWD: A_q += P(slot) * Z_J(stage st); P was written over S by the softmax slot
-    auto issue_pv = [&](int slot, int q, int st, uint32_t uidx, bool first) {
-      mbar_wait(bar_sm_done(slot, 0), uidx & 1);
+    // BWD: A_q += P(sg) * Z_J(stage st); P was written over S by the softmax team
+    auto issue_pv = [&](uint32_t sg, int q, int st, bool first) {
+      int buf;
+      uint32_t ph;
+      s_tile_slot<NQ, NB>(sg, buf, ph);
+      mbar_wait(bar_sm_done(buf), ph);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + C::TMEM_DZ0 + q * D;
-      const uint32_t a_tmem = tmem_base + C::TMEM_S0 + slot * 128;
+      const uint32_t a_tmem = tmem_base + buf * 128;
       const uint64_t bd = sdesc_mn + ((sK + st * C::TILE_BYTES) >> 4);
       if (elect_one()) {
 #pragma unroll
@@ -229,10 +260,6 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
       __syncwarp();
     };
-    auto commit = [&](uint32_t bar) {
-      if (elect_one()) umma_commit(bar);
-      __syncwarp();
-    };
 
 #pragma unroll 1
     for (long long it = it_begin; it < it_end;) {
@@ -240,82 +267,68 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int n = int(min((long long)(p.nkt - j0), it_end - it));
       mbar_wait(bar_q_full, useg & 1);
       tc_fence_after();
+      const int ns = n * NQ;            // S tiles of this segment, local index s = jj*NQ + q
+      const uint32_t sg0 = t * NQ;      // running index of the first one
+      // S tile s of the segment: waits for its K stage if it is the first to touch it
+      auto issue_s_local = [&](int s) {
+        const int jj = s / NQ, q = s % NQ;
+        const uint32_t tk = t + jj;
+        const int st = tk % NST;
+        if (q == 0) {
+          mbar_wait(bar_k_full(st), (tk / NST) & 1);
+          tc_fence_after();
+        }
+        issue_s(sg0 + s, q, st);
+      };
       if (!BWD) {
 #pragma unroll 1
-        for (int jj = 0; jj < n; ++jj, ++t) {
-          const int st = t % NST;
-          mbar_wait(bar_k_full(st), (t / NST) & 1);
-          tc_fence_after();
-          if (NQ == 2) {
-            issue_s(0, 0, st);
-            issue_s(1, 1, st);
-          } else {
-            issue_s(sig & 1, 0, st);
-          }
-          commit(bar_k_empty(st));
+        for (int s = 0; s < ns; ++s) {
+          issue_s_local(s);
+          if (s % NQ == NQ - 1) commit(bar_k_empty((t + s / NQ) % NST));
         }
         commit(bar_q_empty);
       } else {
-        // S tiles of this segment in issue order: sigma = 0 .. ns-1;
-        // NQ == 2: sigma -> (key tile sigma >> 1, slot = Q tile = sigma & 1)
-        // NQ == 1: sigma -> (key tile sigma, slot alternates with the running count)
-        const int ns = n * NQ;
-        const uint32_t t0 = t;
-        const uint32_t slot_base = (NQ == 1) ? (sig & 1) : 0;
-        auto slot_of = [&](int sg) { return (NQ == 2) ? (sg & 1) : int((slot_base + sg) & 1); };
-        auto q_of = [&](int sg) { return (NQ == 2) ? (sg & 1) : 0; };
-        auto kt_of = [&](int sg) { return (NQ == 2) ? (sg >> 1) : sg; };
-        uint32_t upv0 = u0, upv1 = u1;  // per-slot index of the next P to consume
-        auto issue_s_sigma = [&](int sg) {
-          const uint32_t tk = t0 + kt_of(sg);
-          const int st = tk % NST;
-          if (NQ == 1 || (sg & 1) == 0) {  // first S tile that touches this key stage
-            mbar_wait(bar_k_full(st), (tk / NST) & 1);
-            tc_fence_after();
-          }
-          issue_s(slot_of(sg), q_of(sg), st);
-        };
-        issue_s_sigma(0);
-        if (ns > 1) issue_s_sigma(1);
-        if (ns <= 2) commit(bar_q_empty);
+        // NB S tiles are kept in flight ahead of the P.Z products (P aliases its S buffer, and
+        // tcgen05 ops execute in issue order, so S tile s+NB may be issued right after P.Z of s)
+        const int la = ns < NB ? ns : NB;
+        for (int s = 0; s < la; ++s) issue_s_local(s);
+        if (ns <= NB) commit(bar_q_empty);
         // accumulators of the previous segment must have been flushed
         mbar_wait(bar_dz_free, (useg & 1) ^ 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int sg = 0; sg < ns; ++sg) {
-          const int slot = slot_of(sg), q = q_of(sg);
-          const uint32_t tk = t0 + kt_of(sg);
-          const int st = tk % NST;
-          const bool first = (NQ == 2) ? (sg < 2) : (sg == 0);
-          issue_pv(slot, q, st, slot ? upv1 : upv0, first);
-          if (slot) ++upv1; else ++upv0;
-          if (NQ == 1 || (sg & 1) == 1) commit(bar_k_empty(st));  // last reader of the stage
-          if (sg + 2 < ns) {
-            issue_s_sigma(sg + 2);
-            if (sg + 3 >= ns) commit(bar_q_empty);  // that was the last read of the Q tiles
+        for (int s = 0; s < ns; ++s) {
+          const int jj = s / NQ, q = s % NQ;
+          const int st = (t + jj) % NST;
+          issue_pv(sg0 + s, q, st, jj == 0);
+          if (q == NQ - 1) commit(bar_k_empty(st));  // last reader of the stage
+          if (s + NB < ns) {
+            issue_s_local(s + NB);
+            if (s + NB == ns - 1) commit(bar_q_empty);  // that was the last read of the Q tiles
           }
         }
         commit(bar_dz_full);
-        t = t0 + n;
       }
+      t += n;
       it += n;
       ++useg;
     }
   } else if (warp >= 4) {
-    // =========================== softmax slots ===========================
+    // =========================== softmax teams ===========================
     const int sw = warp - 4;
-    const int slot = sw >> 3;         // which S stream
+    const int team = sw >> 3;         // which S tiles (sigma & 1 == team)
     const int half = (sw >> 2) & 1;   // which 64 key columns of each S tile
     const int w4 = warp & 3;          // TMEM lane quarter this warp may touch
     const int row_in_tile = w4 * 32 + lane;
     const uint32_t lane_base = tmem_base + (uint32_t(w4 * 32) << 16);
     const float c1 = p.c1;
-    uint32_t t = 0, useg = 0, sig = 0, uu = 0;  // uu: S tiles consumed by this slot
+    uint32_t t = 0, useg = 0;
 
+#pragma unroll 1
     for (long long it = it_begin; it < it_end;) {
       const int rb = int(it / p.nkt), j0 = int(it % p.nkt);
       const int n = int(min((long long)(p.nkt - j0), it_end - it));
-      const int q = (NQ == 2) ? slot : 0;
+      const int q = (NQ == 2) ? team : 0;
       const int row = rb * C::RB_ROWS + q * 128 + row_in_tile;  // anchor row (local)
       const bool valid = row < p.m_loc;
       const int grow = p.row_global_base + row;                 // same row in key space
@@ -324,14 +337,17 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int gpos = row < p.pos_split ? grow + p.pos_delta : grow - p.pos_delta;
       float r_i = 0.f;
       if (BWD && valid) r_i = __ldg(p.r_row + row);
-      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-      const uint32_t slot_base = (NQ == 1) ? (sig & 1) : 0;
+      float2 acc01 = make_float2(0.f, 0.f), acc23 = make_float2(0.f, 0.f);
 
+#pragma unroll 1
       for (int jj = 0; jj < n; ++jj) {
-        if (NQ == 1 && int((slot_base + jj) & 1) != slot) continue;
         const uint32_t tk = t + jj;
+        const uint32_t sg = (NQ == 2) ? tk * 2 + team : tk;
+        if (NQ == 1 && int(sg & 1) != team) continue;
         const int st = tk % NST;
-        const int ub = uu % SBUF;
+        int buf;
+        uint32_t ph;
+        s_tile_slot<NQ, NB>(sg, buf, ph);
         const int k0 = (j0 + jj) * C::KT;
         // tiles that hold a diagonal entry, a positive (a Q tile may straddle the view
         // boundary, so test both placements) or keys past the end need per-element predicates
@@ -339,9 +355,9 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
         special = special || (k0 < g0 - p.pos_delta + 128 && g0 - p.pos_delta < k0 + C::KT) ||
                   (k0 < g0 + p.pos_delta + 128 && g0 + p.pos_delta < k0 + C::KT);
         if (BWD) mbar_wait(bar_k_full(st), (tk / NST) & 1);  // r_j of this stage has landed
-        mbar_wait(bar_s_full(slot, ub), (uu / SBUF) & 1);
+        mbar_wait(bar_s_full(buf), ph);
         tc_fence_after();
-        const uint32_t s_addr = lane_base + C::TMEM_S0 + (slot * SBUF + ub) * 128 + half * 64;
+        const uint32_t s_addr = lane_base + buf * 128 + half * 64;
         const float* rk = rk_gen + st * C::KT + half * 64;
         const int kbase = k0 + half * 64;
 
@@ -354,33 +370,46 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
           tc_wait_ld();
 #pragma unroll
           for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));
+          // packed f32x2 math throughout (FFMA2 / FADD2 / FMUL2): half the FMA-pipe issue slots
+          constexpr int POLY = BWD ? MAAI_POLY_BWD : MAAI_POLY_FWD;
+          constexpr int DEG = BWD ? 3 : 4;
+          const float2 c1p = make_float2(c1, c1), c1n = make_float2(-c1, -c1);
+          float2 e[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            v[i] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(v[i]), c1, -c1)));
+          for (int j = 0; j < 16; ++j) {
+            const float2 x = __ffma2_rn(
+                make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), c1p, c1n);
+            if ((j & 7) < POLY) {
+              e[j] = exp2_poly2<DEG>(x);
+            } else {
+              e[j].x = ex2_approx(x.x);
+              e[j].y = ex2_approx(x.y);
+            }
+          }
           if (special) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int kc = kbase + c * 32 + i;
-              if (kc == grow || kc == gpos || kc >= p.m_glob) v[i] = 0u;
+            for (int j = 0; j < 16; ++j) {
+              const int kc = kbase + c * 32 + 2 * j;
+              if (kc == grow || kc == gpos || kc >= p.m_glob) e[j].x = 0.f;
+              if (kc + 1 == grow || kc + 1 == gpos || kc + 1 >= p.m_glob) e[j].y = 0.f;
             }
           }
           if (!BWD) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              acc0 += __uint_as_float(v[i]);
-              acc1 += __uint_as_float(v[i + 1]);
-              acc2 += __uint_as_float(v[i + 2]);
-              acc3 += __uint_as_float(v[i + 3]);
+            for (int j = 0; j < 16; j += 2) {
+              acc01 = __fadd2_rn(acc01, e[j]);
+              acc23 = __fadd2_rn(acc23, e[j + 1]);
             }
           } else {
             uint32_t pk[16];
+            const float2 ri2 = make_float2(r_i, r_i);
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 rj = *reinterpret_cast<const float4*>(rk + c * 32 + i);
-              pk[i / 2] = pack_bf16x2(__uint_as_float(v[i]) * (r_i + rj.x),
-                                      __uint_as_float(v[i + 1]) * (r_i + rj.y));
-              pk[i / 2 + 1] = pack_bf16x2(__uint_as_float(v[i + 2]) * (r_i + rj.z),
-                                          __uint_as_float(v[i + 3]) * (r_i + rj.w));
+            for (int j = 0; j < 16; j += 2) {
+              const float4 rj = *reinterpret_cast<const float4*>(rk + c * 32 + 2 * j);
+              const float2 p0 = __fmul2_rn(e[j], __fadd2_rn(ri2, make_float2(rj.x, rj.y)));
+              const float2 p1 = __fmul2_rn(e[j + 1], __fadd2_rn(ri2, make_float2(rj.z, rj.w)));
+              pk[j] = pack_bf16x2(p0.x, p0.y);
+              pk[j + 1] = pack_bf16x2(p1.x, p1.y);
             }
             // P (bf16, 2 keys per column) overwrites S columns this warpgroup has already read:
             // keys [half*64 + c*32, +32) -> columns half*64 + c*16 .. +16
@@ -390,41 +419,45 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
         if (BWD) tc_wait_st();
         tc_fence_before();
-        mbar_arrive(bar_sm_done(slot, ub));
-        ++uu;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sm_done(buf));
       }
 
       if (!BWD) {
-        if (valid) atomicAdd(p.l_out + row, (acc0 + acc1) + (acc2 + acc3));
+        if (valid) atomicAdd(p.l_out + row, (acc01.x + acc01.y) + (acc23.x + acc23.y));
       } else {
         mbar_wait(bar_dz_full, useg & 1);
         tc_fence_after();
-        // NQ == 2: slot s owns accumulator s (D columns), its two warpgroups flush D/2 each;
-        // NQ == 1: the four warpgroups flush 64 columns each of the single 256-column accumulator
-        constexpr int NCOL = (NQ == 2) ? D / 2 : 64;
-        const int col0 = (NQ == 2) ? half * NCOL : (slot * 2 + half) * 64;
-        const uint32_t a_addr = lane_base + C::TMEM_DZ0 + ((NQ == 2) ? slot * D : 0) + col0;
+        // NQ == 2: team t owns accumulator t (D columns), its two warpgroups flush D/2 each;
+        // NQ == 1: the four warpgroups share the single accumulator, max(D/4, 32) columns each
+        constexpr int NCOL = (NQ == 2) ? D / 2 : (D / 4 >= 32 ? D / 4 : 32);
+        const int wg = team * 2 + half;
+        const int col0 = (NQ == 2) ? half * NCOL : wg * NCOL;
+        const bool has_cols = col0 < D;
+        const uint32_t a_addr = lane_base + C::TMEM_DZ0 + ((NQ == 2) ? team * D : 0) + col0;
+        if (has_cols) {
 #pragma unroll
-        for (int c = 0; c < NCOL / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_x32(a_addr + c * 32, v);
-          tc_wait_ld();
+          for (int c = 0; c < NCOL / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_x32(a_addr + c * 32, v);
+            tc_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));
-          if (valid) {
-            float* dst = p.dz_acc + (size_t)row * D + col0 + c * 32;
+            for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));
+            if (valid) {
+              float* dst = p.dz_acc + (size_t)row * D + col0 + c * 32;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              atomicAdd(reinterpret_cast<float4*>(dst + i),
-                        make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
-                                    __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+              for (int i = 0; i < 32; i += 4)
+                atomicAdd(reinterpret_cast<float4*>(dst + i),
+                          make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                      __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+            }
           }
         }
         tc_fence_before();
-        mbar_arrive(bar_dz_free);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_dz_free);
       }
       t += n;
-      sig += n * NQ;
       it += n;
       ++useg;
     }

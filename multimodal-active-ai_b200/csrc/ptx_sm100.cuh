@@ -223,6 +223,38 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// exp2 on the FMA/ALU pipes for a pair of arguments in [-126, 1): Cody-Waite split with the
+// 1.5*2^23 magic number (t = x + magic rounds x to the nearest integer n in the low mantissa bits,
+// f = x - n in [-0.5, 0.5]), minimax polynomial for 2^f (max rel. error 7.5e-5 for degree 3,
+// 2.7e-6 for degree 4, fitted offline), exponent re-inserted by adding n << 23 to the bits of p.
+// This takes work off the 16-lane/clk MUFU unit, which is what bounds the softmax stage
+// (profiles/r1_ncu_summary_v1.md: XU pipe 77 % busy, FMA pipe 21 %).  Callers guarantee
+// x >= -126 (temperature >= 0.025 and |cos| <= 1 + bf16 rounding).
+template <int DEG>
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+  float2 pl;
+  if (DEG == 3) {
+    pl = __ffma2_rn(f, make_float2(5.517165389e-02f, 5.517165389e-02f),
+                    make_float2(2.426111210e-01f, 2.426111210e-01f));
+    pl = __ffma2_rn(pl, f, make_float2(6.932609883e-01f, 6.932609883e-01f));
+    pl = __ffma2_rn(pl, f, make_float2(9.999280737e-01f, 9.999280737e-01f));
+  } else {
+    pl = __ffma2_rn(f, make_float2(9.570100157e-03f, 9.570100157e-03f),
+                    make_float2(5.591786018e-02f, 5.591786018e-02f));
+    pl = __ffma2_rn(pl, f, make_float2(2.402474487e-01f, 2.402474487e-01f));
+    pl = __ffma2_rn(pl, f, make_float2(6.931218148e-01f, 6.931218148e-01f));
+    pl = __ffma2_rn(pl, f, make_float2(9.999992614e-01f, 9.999992614e-01f));
+  }
+  float2 r;
+  r.x = __int_as_float(__float_as_int(pl.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(pl.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
 // two fp32 -> packed bf16x2 (lo in bits [0,16), hi in bits [16,32)), round to nearest even
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
