@@ -121,10 +121,24 @@ def run_reference(args, rank):
         "e2e": {"value": r["pairs_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
+_REAL_STDOUT = sys.stdout
 
 
 def main():
+    # Exactly one line may reach stdout (the JSON): libraries such as NCCL print banners there, so
+    # fd 1 is pointed at stderr for the whole run and the JSON goes to the saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -314,7 +328,7 @@ def main():
         }
         if secondary:
             line["config"]["configs1_4096_pairs"] = secondary
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
