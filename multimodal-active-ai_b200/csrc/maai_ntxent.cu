@@ -289,4 +289,11 @@ int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, 
   return MAAI_OK;
 }
 
+#if MAAI_PROF
+// tools/phase_prof.py: per-CTA, per-warp phase cycle counters of the last tile-kernel launch
+int maai_debug_prof_read(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, maai::g_prof, sizeof(long long) * n);
+}
+#endif
+
 }  // extern "C"

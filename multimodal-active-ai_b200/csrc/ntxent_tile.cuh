@@ -26,29 +26,77 @@
 //                   (S = Q K^T into TMEM; BWD also A += P Z_J with P read from TMEM and Z_J read
 //                   from the *same* smem tile as an MN-major operand)
 //   warp 2        : TMEM allocator
-//   warps 4-11 / 12-19 : two softmax "teams" of 256 threads.  A team owns one S tile at a time; its
-//                   two warpgroups split the 128 key columns (64 each), one TMEM lane (= anchor
-//                   row) per thread: tcgen05.ld S -> exp2 -> row sum (FWD) / P = E (r_i + r_j) ->
-//                   bf16 -> TMEM over the S columns already consumed (BWD).
-// NQ == 2 (two 128-row Q tiles per row block, team t owns Q tile t, each K tile feeds both): halves
-//   the L2 -> smem traffic per flop; used by the MUFU-bound forward.
-// NQ == 1 (one Q tile, teams take alternate key tiles): leaves TMEM room for three S buffers next
-//   to the accumulator, so the tensor pipe always has another tile's MMAs to run while a softmax
-//   is in flight; used by the backward (profiles/r1_ncu_summary_v1.md shows the exposed
-//   S -> softmax -> P -> PV chain of the one-buffer-per-Q-tile layout).
+//   warps 4-19    : 16 softmax warps, one TMEM lane (= anchor row) per thread:
+//                   tcgen05.ld S -> exp2 -> row sum (FWD) / P = E (r_i + r_j) -> bf16 -> TMEM over
+//                   the S columns already consumed (BWD).
+// NQ == 2 (two 128-row Q tiles per row block, each K tile feeds both): halves the L2 -> smem
+//   traffic per flop; used by the MUFU-bound forward.  The softmax warps form two teams of 8;
+//   team t owns Q tile t and its two warpgroups split the 128 key columns (64 per thread).
+// NQ == 1 (one Q tile): leaves TMEM room for three S buffers next to the accumulator, so the
+//   tensor pipe always has another tile's MMAs to run while a softmax is in flight; used by the
+//   backward (profiles/r1_ncu_summary_v1.md shows the exposed S -> softmax -> P -> PV chain of the
+//   one-buffer-per-Q-tile layout).  All 16 softmax warps work on every S tile (32 columns per
+//   thread), which halves the latency of the softmax stage of each tile.
 #pragma once
 #include "ptx_sm100.cuh"
 
 // Of every 8 column pairs a softmax thread handles, this many take the polynomial exp2 on the FMA
 // pipe instead of MUFU.EX2 (build-time knobs so the split can be A/B-measured).
 #ifndef MAAI_POLY_FWD
-#define MAAI_POLY_FWD 3
+#define MAAI_POLY_FWD 4
 #endif
 #ifndef MAAI_POLY_BWD
 #define MAAI_POLY_BWD 0
 #endif
+// Optional second split for the odd softmax warpgroups (two of the four warps of every SM
+// sub-partition): lets MUFU-heavy and FMA-heavy warps share a scheduler.  Default: same split.
+#ifndef MAAI_POLY_FWD_B
+#define MAAI_POLY_FWD_B MAAI_POLY_FWD
+#endif
+#ifndef MAAI_POLY_BWD_B
+#define MAAI_POLY_BWD_B MAAI_POLY_BWD
+#endif
+#ifndef MAAI_POLY_DEG_FWD
+#define MAAI_POLY_DEG_FWD 3
+#endif
+#ifndef MAAI_POLY_DEG_BWD
+#define MAAI_POLY_DEG_BWD 3
+#endif
+// Timing-only ablations (results are WRONG when non-zero; tools/ablate.py): bit 0 no exp,
+// bit 1 no P.Z MMAs, bit 2 no S MMAs, bit 3 no r_j loads.
+#ifndef MAAI_ABL
+#define MAAI_ABL 0
+#endif
+
+// Per-warp phase timers (clock64) for tools/phase_prof.py; compiled out unless MAAI_PROF=1.
+#ifndef MAAI_PROF
+#define MAAI_PROF 0
+#endif
 
 namespace maai {
+
+#if MAAI_PROF
+__device__ long long g_prof[160 * 20 * 8];
+#define PROF_INIT()                                  \
+  long long prof_t = clock64();                      \
+  long long prof_a[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF_MARK(i)                                 \
+  do {                                               \
+    const long long _n = clock64();                  \
+    prof_a[i] += _n - prof_t;                        \
+    prof_t = _n;                                     \
+  } while (0)
+#define PROF_FLUSH()                                                          \
+  do {                                                                        \
+    if ((threadIdx.x & 31) == 0)                                              \
+      for (int _i = 0; _i < 8; ++_i)                                          \
+        g_prof[((size_t)blockIdx.x * 20 + (threadIdx.x >> 5)) * 8 + _i] = prof_a[_i]; \
+  } while (0)
+#else
+#define PROF_INIT() do { } while (0)
+#define PROF_MARK(i) do { } while (0)
+#define PROF_FLUSH() do { } while (0)
+#endif
 
 struct TileParams {
   int m_loc;             // anchor rows covered by tmap_q
@@ -77,7 +125,10 @@ struct TileCfg {
   static constexpr int CHUNKS = D / 64;                // 128-byte swizzle chunks per row
   static constexpr int CHUNK_BYTES = 128 * 128;        // 128 rows x 128 B
   static constexpr int TILE_BYTES = CHUNKS * CHUNK_BYTES;
-  static constexpr int NST = (D == 256) ? 2 : 4;       // K ring depth
+  // K ring depth.  A stage lives from its S MMA until its P.Z MMA has completed, i.e. about NB + 1
+  // tile periods in the backward, so the ring must be deeper than that for the TMA prefetch to run
+  // ahead (with 4 stages and NB = 3 the load latency was exposed on every tile).
+  static constexpr int NST = (D == 256) ? 2 : (D == 64 ? 8 : ((NQ == 1 || !BWD) ? 5 : 4));
   // S buffers (128 TMEM columns each).  FWD: all of TMEM.  BWD: what the accumulators leave.
   static constexpr int NB = !BWD ? 4 : (NQ == 2 ? 2 : (D <= 128 ? 3 : 2));
   static constexpr int TMEM_DZ0 = NB * 128;            // BWD accumulators: DZ0 + q*D
@@ -87,10 +138,11 @@ struct TileCfg {
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + NQ * TILE_BYTES;
   static constexpr int OFF_RK = OFF_K + NST * TILE_BYTES;
-  static constexpr int OFF_BAR = OFF_RK + NST * KT * 4;
+  static constexpr int OFF_BAR = OFF_RK + (BWD ? NST * KT * 4 : 0);  // r_j ring: backward only
   static constexpr int NBAR = 2 + 2 * NST + 2 * NB + 2;
   static constexpr int OFF_TMEMPTR = OFF_BAR + NBAR * 8;
   static constexpr int SMEM_BYTES = OFF_TMEMPTR + 16 + 1024;  // + alignment slack
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB per CTA)");
 };
 
 // TMEM buffer and mbarrier phase of the S tile with CTA-wide running index `sg`.
@@ -104,6 +156,88 @@ __device__ __forceinline__ void s_tile_slot(uint32_t sg, int& buf, uint32_t& pha
     buf = int(sg % NB);
     phase = (sg / NB) & 1;
   }
+}
+
+// One 16-column chunk of one TMEM lane (= anchor row) of an S tile, already in registers: E -> row
+// sum (FWD) or P = E (r_i + r_j) -> bf16 -> tcgen05.st (BWD).  Of the 8 column pairs, POLY take the
+// polynomial exp2 on the FMA pipe, the rest MUFU.EX2.  The polynomial path yields E * 2^c1 (see
+// exp2_dot_poly2); FWD keeps those in their own accumulators, BWD folds 2^-c1 into (r_i + r_j).
+struct ChunkCtx {
+  float c1;        // log2(e) / tau
+  float kscale;    // 2^-c1
+  float r_i;       // BWD: row factor of this anchor
+  float r_ik;      // BWD: r_i * 2^-c1
+  int grow, gpos;  // key indices of this anchor's diagonal / positive entry
+  int m_glob;
+#if MAAI_PROF
+  long long prof_t;
+  long long prof_a[8];
+#endif
+};
+#if MAAI_PROF
+#define CX_MARK(i)                                   \
+  do {                                               \
+    const long long _n = clock64();                  \
+    cx.prof_a[i] += _n - cx.prof_t;                  \
+    cx.prof_t = _n;                                  \
+  } while (0)
+#else
+#define CX_MARK(i) do { } while (0)
+#endif
+template <bool BWD, int POLY, int DEG>
+__device__ __forceinline__ void softmax_chunk(uint32_t (&v)[16], uint32_t st_addr, const float* rk,
+                                              ChunkCtx& cx, bool special, int kc0,
+                                              float2 (&acc_m)[2], float2 (&acc_p)[2]) {
+  // packed f32x2 math throughout (FFMA2 / FADD2 / FMUL2): half the FMA-pipe issue slots
+  const float2 c1p = make_float2(cx.c1, cx.c1), c1n = make_float2(-cx.c1, -cx.c1);
+  float2 e[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 sv = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+    if (MAAI_ABL & 1) {
+      e[j] = __ffma2_rn(sv, c1p, c1n);
+    } else if (j < POLY) {
+      e[j] = exp2_dot_poly2<DEG>(sv, c1p);
+    } else {
+      const float2 x = __ffma2_rn(sv, c1p, c1n);
+      e[j].x = ex2_approx(x.x);
+      e[j].y = ex2_approx(x.y);
+    }
+  }
+  if (special) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kc = kc0 + 2 * j;
+      if (kc == cx.grow || kc == cx.gpos || kc >= cx.m_glob) e[j].x = 0.f;
+      if (kc + 1 == cx.grow || kc + 1 == cx.gpos || kc + 1 >= cx.m_glob) e[j].y = 0.f;
+    }
+  }
+  if (!BWD) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < POLY) acc_p[j & 1] = __fadd2_rn(acc_p[j & 1], e[j]);
+      else acc_m[j & 1] = __fadd2_rn(acc_m[j & 1], e[j]);
+    }
+  } else {
+    uint32_t pk[8];
+    const float2 ri2 = make_float2(cx.r_i, cx.r_i), rik2 = make_float2(cx.r_ik, cx.r_ik);
+    const float2 ks2 = make_float2(cx.kscale, cx.kscale);
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      float4 rj = (MAAI_ABL & 8) ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                 : *reinterpret_cast<const float4*>(rk + 2 * j);
+      const float2 rj0 = make_float2(rj.x, rj.y), rj1 = make_float2(rj.z, rj.w);
+      const float2 w0 = (j < POLY) ? __ffma2_rn(rj0, ks2, rik2) : __fadd2_rn(ri2, rj0);
+      const float2 w1 = (j + 1 < POLY) ? __ffma2_rn(rj1, ks2, rik2) : __fadd2_rn(ri2, rj1);
+      const float2 p0 = __fmul2_rn(e[j], w0);
+      const float2 p1 = __fmul2_rn(e[j + 1], w1);
+      pk[j] = pack_bf16x2(p0.x, p0.y);
+      pk[j + 1] = pack_bf16x2(p1.x, p1.y);
+    }
+    // P (bf16, 2 keys per column) overwrites S columns this thread has already read
+    tmem_st_x8(st_addr, pk);
+  }
+  CX_MARK(2);
 }
 
 template <int D, bool BWD, int NQ>
@@ -150,7 +284,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
     for (int u = 0; u < NB; ++u) {
       mbar_init(bar_s_full(u), 1);
-      mbar_init(bar_sm_done(u), 8);  // one arrive per warp of the team (8 warps)
+      mbar_init(bar_sm_done(u), NQ == 2 ? 8 : 16);  // one arrive per warp working on the tile
     }
     mbar_init(bar_dz_full, 1);
     mbar_init(bar_dz_free, 16);      // one arrive per softmax warp
@@ -172,11 +306,13 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
+      PROF_INIT();
       uint32_t t = 0, useg = 0;
       for (long long it = it_begin; it < it_end;) {
         const int rb = int(it / p.nkt), j0 = int(it % p.nkt);
         const int n = int(min((long long)(p.nkt - j0), it_end - it));
         mbar_wait(bar_q_empty, (useg & 1) ^ 1);
+        PROF_MARK(0);
         mbar_arrive_expect_tx(bar_q_full, NQ * C::TILE_BYTES);
 #pragma unroll
         for (int q = 0; q < NQ; ++q)
@@ -187,6 +323,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
         for (int jj = 0; jj < n; ++jj, ++t) {
           const int st = t % NST;
           mbar_wait(bar_k_empty(st), ((t / NST) & 1) ^ 1);
+          PROF_MARK(1);
           mbar_arrive_expect_tx(bar_k_full(st), C::TILE_BYTES + (BWD ? C::KT * 4 : 0));
 #pragma unroll
           for (int c = 0; c < C::CHUNKS; ++c)
@@ -195,10 +332,12 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
           if (BWD)
             bulk_load_1d(sRK + st * C::KT * 4, p.r_col + (size_t)(j0 + jj) * C::KT, C::KT * 4,
                          bar_k_full(st));
+          PROF_MARK(2);
         }
         it += n;
         ++useg;
       }
+      PROF_FLUSH();
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -212,6 +351,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const uint64_t sdesc_mn = make_sdesc_sw128(0, p.pv_lbo, p.pv_sbo);  // MN-major Z_J for P.Z
     uint32_t t = 0;     // key tiles consumed so far (K ring position); S-tile index = t*NQ + q
     uint32_t useg = 0;
+    PROF_INIT();
 
     auto commit = [&](uint32_t bar) {
       if (elect_one()) umma_commit(bar);
@@ -225,19 +365,23 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       if (!BWD) {  // FWD: wait until the softmax team has drained this buffer's previous tile
         mbar_wait(bar_sm_done(buf), ph ^ 1);
         tc_fence_after();
+        PROF_MARK(1);
       }
       const uint32_t d_tmem = tmem_base + buf * 128;
       const uint64_t ad = sdesc_k + ((sQ + q * C::TILE_BYTES) >> 4);
       const uint64_t bd = sdesc_k + ((sK + st * C::TILE_BYTES) >> 4);
       if (elect_one()) {
+        if (!(MAAI_ABL & 4)) {
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint32_t off = ((k >> 2) * C::CHUNK_BYTES + (k & 3) * 32) >> 4;
-          umma_ss(d_tmem, ad + off, bd + off, IDESC_S, k > 0);
+          for (int k = 0; k < D / 16; ++k) {
+            const uint32_t off = ((k >> 2) * C::CHUNK_BYTES + (k & 3) * 32) >> 4;
+            umma_ss(d_tmem, ad + off, bd + off, IDESC_S, k > 0);
+          }
         }
         umma_commit(bar_s_full(buf));
       }
       __syncwarp();
+      PROF_MARK(2);
     };
     // BWD: A_q += P(sg) * Z_J(stage st); P was written over S by the softmax team
     auto issue_pv = [&](uint32_t sg, int q, int st, bool first) {
@@ -246,19 +390,24 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       s_tile_slot<NQ, NB>(sg, buf, ph);
       mbar_wait(bar_sm_done(buf), ph);
       tc_fence_after();
+      PROF_MARK(1);
       const uint32_t d_tmem = tmem_base + C::TMEM_DZ0 + q * D;
       const uint32_t a_tmem = tmem_base + buf * 128;
       const uint64_t bd = sdesc_mn + ((sK + st * C::TILE_BYTES) >> 4);
-      if (elect_one()) {
+      if (!(MAAI_ABL & 2) && elect_one()) {
 #pragma unroll
         for (int k = 0; k < C::KT / 16; ++k) {
-          // 16 keys = 16 smem rows of 128 B (2048 B); P of key half h (64 keys, 32 packed
-          // columns) sits at S columns [h*64, h*64+32)
-          umma_ts(d_tmem, a_tmem + (k >> 2) * 64 + (k & 3) * 8, bd + k * (2048 >> 4), IDESC_PV,
+          // 16 keys = 16 smem rows of 128 B (2048 B).  P (2 keys per 32-bit column) of each
+          // thread's key range sits at the start of that range's S columns:
+          // NQ == 2: 64 keys per warpgroup -> key half h at columns [h*64, h*64+32)
+          // NQ == 1: 32 keys per warpgroup -> key quarter c at columns [c*32, c*32+16)
+          const uint32_t pcol = (NQ == 2) ? (k >> 2) * 64 + (k & 3) * 8 : (k >> 1) * 32 + (k & 1) * 8;
+          umma_ts(d_tmem, a_tmem + pcol, bd + k * (2048 >> 4), IDESC_PV,
                   (first && k == 0) ? 0u : 1u);
         }
       }
       __syncwarp();
+      PROF_MARK(3);
     };
 
 #pragma unroll 1
@@ -267,6 +416,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int n = int(min((long long)(p.nkt - j0), it_end - it));
       mbar_wait(bar_q_full, useg & 1);
       tc_fence_after();
+      PROF_MARK(0);
       const int ns = n * NQ;            // S tiles of this segment, local index s = jj*NQ + q
       const uint32_t sg0 = t * NQ;      // running index of the first one
       // S tile s of the segment: waits for its K stage if it is the first to touch it
@@ -277,6 +427,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (q == 0) {
           mbar_wait(bar_k_full(st), (tk / NST) & 1);
           tc_fence_after();
+          PROF_MARK(0);
         }
         issue_s(sg0 + s, q, st);
       };
@@ -296,6 +447,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
         // accumulators of the previous segment must have been flushed
         mbar_wait(bar_dz_free, (useg & 1) ^ 1);
         tc_fence_after();
+        PROF_MARK(4);
 #pragma unroll 1
         for (int s = 0; s < ns; ++s) {
           const int jj = s / NQ, q = s % NQ;
@@ -312,17 +464,43 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       t += n;
       it += n;
       ++useg;
+      PROF_MARK(5);
     }
+    PROF_FLUSH();
   } else if (warp >= 4) {
-    // =========================== softmax teams ===========================
+    // =========================== softmax warps ===========================
     const int sw = warp - 4;
-    const int team = sw >> 3;         // which S tiles (sigma & 1 == team)
-    const int half = (sw >> 2) & 1;   // which 64 key columns of each S tile
+    const int wgi = sw >> 2;                          // softmax warpgroup 0..3
+    const int team = (NQ == 2) ? (wgi >> 1) : 0;      // NQ == 2: Q tile owned by this warp
+    constexpr int TCOLS = (NQ == 2) ? 64 : 32;        // key columns per thread per S tile
+    constexpr int NCH = TCOLS / 16;                   // 16-column register chunks per S tile
+    constexpr int MODB = (NQ == 2) ? NB / 2 : NB;     // S buffers this warp cycles through
+    const int col_off = (NQ == 2) ? (wgi & 1) * 64 : wgi * 32;  // first key column of this thread
     const int w4 = warp & 3;          // TMEM lane quarter this warp may touch
     const int row_in_tile = w4 * 32 + lane;
-    const uint32_t lane_base = tmem_base + (uint32_t(w4 * 32) << 16);
+    const uint32_t lane_base = tmem_base + (uint32_t(w4 * 32) << 16) + col_off;
     const float c1 = p.c1;
-    uint32_t t = 0, useg = 0;
+    const float kscale = ex2_approx(-c1);  // 2^-c1: what the polynomial path leaves out
+    constexpr int POLY_A = BWD ? MAAI_POLY_BWD : MAAI_POLY_FWD;
+    constexpr int POLY_B = BWD ? MAAI_POLY_BWD_B : MAAI_POLY_FWD_B;
+    constexpr int DEG = BWD ? MAAI_POLY_DEG_BWD : MAAI_POLY_DEG_FWD;
+    // Running ring positions of the next S tile of this warp (kept incrementally: no div / mod
+    // in the per-tile path): S buffer slot + phase, K stage + phase.
+    int sb = 0, kst = 0;
+    uint32_t sph = 0, kph = 0;
+    const int kt_ragged = (p.m_glob & (C::KT - 1)) ? p.nkt - 1 : -8;
+    uint32_t useg = 0;
+    // v0 holds (or is receiving) the first chunk of the next tile when `have` is set
+    uint32_t v0[16], v1[16];
+    bool have = false;
+    ChunkCtx cx;
+    cx.c1 = c1;
+    cx.kscale = kscale;
+    cx.m_glob = p.m_glob;
+#if MAAI_PROF
+    cx.prof_t = clock64();
+    for (int i = 0; i < 8; ++i) cx.prof_a[i] = 0;
+#endif
 
 #pragma unroll 1
     for (long long it = it_begin; it < it_end;) {
@@ -335,106 +513,116 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int g0 = p.row_global_base + rb * C::RB_ROWS + q * 128;
       // key index of this row's positive (masked like the diagonal)
       const int gpos = row < p.pos_split ? grow + p.pos_delta : grow - p.pos_delta;
-      float r_i = 0.f;
-      if (BWD && valid) r_i = __ldg(p.r_row + row);
-      float2 acc01 = make_float2(0.f, 0.f), acc23 = make_float2(0.f, 0.f);
+      // Key tiles that may hold a diagonal entry or a positive of this Q tile (a Q tile may
+      // straddle the view boundary, so both placements) or keys past the end take the
+      // per-element predicates: tiles kt_x and kt_x + 1 of each of the three 128-key windows.
+      const int kt_d = g0 >> 7, kt_p1 = (g0 - p.pos_delta) >> 7, kt_p2 = (g0 + p.pos_delta) >> 7;
+      cx.r_i = (BWD && valid) ? __ldg(p.r_row + row) : 0.f;
+      cx.r_ik = cx.r_i * kscale;
+      cx.grow = grow;
+      cx.gpos = gpos;
+      float2 acc_m[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      float2 acc_p[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 
 #pragma unroll 1
       for (int jj = 0; jj < n; ++jj) {
-        const uint32_t tk = t + jj;
-        const uint32_t sg = (NQ == 2) ? tk * 2 + team : tk;
-        if (NQ == 1 && int(sg & 1) != team) continue;
-        const int st = tk % NST;
-        int buf;
-        uint32_t ph;
-        s_tile_slot<NQ, NB>(sg, buf, ph);
-        const int k0 = (j0 + jj) * C::KT;
-        // tiles that hold a diagonal entry, a positive (a Q tile may straddle the view
-        // boundary, so test both placements) or keys past the end need per-element predicates
-        bool special = (k0 < g0 + 128 && g0 < k0 + C::KT) || (k0 + C::KT > p.m_glob);
-        special = special || (k0 < g0 - p.pos_delta + 128 && g0 - p.pos_delta < k0 + C::KT) ||
-                  (k0 < g0 + p.pos_delta + 128 && g0 + p.pos_delta < k0 + C::KT);
-        if (BWD) mbar_wait(bar_k_full(st), (tk / NST) & 1);  // r_j of this stage has landed
-        mbar_wait(bar_s_full(buf), ph);
-        tc_fence_after();
-        const uint32_t s_addr = lane_base + buf * 128 + half * 64;
-        const float* rk = rk_gen + st * C::KT + half * 64;
-        const int kbase = k0 + half * 64;
+        const int kt = j0 + jj;
+        const int buf = (NQ == 2) ? team * MODB + sb : sb;
+        const bool special = unsigned(kt - kt_d) <= 1u || unsigned(kt - kt_p1) <= 1u ||
+                             unsigned(kt - kt_p2) <= 1u || kt == kt_ragged;
+        const uint32_t s_addr = lane_base + buf * 128;
+        const float* rk = rk_gen + kst * C::KT + col_off;
+        const int kbase = kt * C::KT + col_off;
+        CX_MARK(5);
+        if (!have) {
+          if (BWD) mbar_wait(bar_k_full(kst), kph);  // r_j of this stage has landed
+          mbar_wait(bar_s_full(buf), sph);
+          tc_fence_after();
+          tmem_ld_x16(s_addr, v0);
+        }
+        CX_MARK(0);
+        // ring positions of the tile after this one
+        int sb_n = sb + 1, kst_n = kst + 1;
+        uint32_t sph_n = sph, kph_n = kph;
+        if (sb_n == MODB) { sb_n = 0; sph_n ^= 1; }
+        if (kst_n == NST) { kst_n = 0; kph_n ^= 1; }
+        have = false;
 
+        // Chunks are double-buffered in registers: the tcgen05.ld of chunk c + 1 (or of the next
+        // tile's first chunk, if its S tile is already complete) is in flight while chunk c is
+        // processed.  keys [col_off + c*16, +16) -> P columns col_off + c*8 .. +8.
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          // single-buffered on purpose: four softmax warps per SM sub-partition cover the
-          // tcgen05.ld latency, and 64 live S registers would spill under the 640-thread cap
-          uint32_t v[32];
-          tmem_ld_x32(s_addr + c * 32, v);
+        for (int c = 0; c < NCH; c += 2) {
           tc_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));
-          // packed f32x2 math throughout (FFMA2 / FADD2 / FMUL2): half the FMA-pipe issue slots
-          constexpr int POLY = BWD ? MAAI_POLY_BWD : MAAI_POLY_FWD;
-          constexpr int DEG = BWD ? 3 : 4;
-          const float2 c1p = make_float2(c1, c1), c1n = make_float2(-c1, -c1);
-          float2 e[16];
+          for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(v0[i]));
+          tmem_ld_x16(s_addr + (c + 1) * 16, v1);
+          CX_MARK(1);
+          if (POLY_A == POLY_B || !(wgi & 1))
+            softmax_chunk<BWD, POLY_A, DEG>(v0, s_addr + c * 8, rk + c * 16, cx, special,
+                                            kbase + c * 16, acc_m, acc_p);
+          else
+            softmax_chunk<BWD, POLY_B, DEG>(v0, s_addr + c * 8, rk + c * 16, cx, special,
+                                            kbase + c * 16, acc_m, acc_p);
+          tc_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 x = __ffma2_rn(
-                make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), c1p, c1n);
-            if ((j & 7) < POLY) {
-              e[j] = exp2_poly2<DEG>(x);
-            } else {
-              e[j].x = ex2_approx(x.x);
-              e[j].y = ex2_approx(x.y);
-            }
-          }
-          if (special) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int kc = kbase + c * 32 + 2 * j;
-              if (kc == grow || kc == gpos || kc >= p.m_glob) e[j].x = 0.f;
-              if (kc + 1 == grow || kc + 1 == gpos || kc + 1 >= p.m_glob) e[j].y = 0.f;
-            }
-          }
-          if (!BWD) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              acc01 = __fadd2_rn(acc01, e[j]);
-              acc23 = __fadd2_rn(acc23, e[j + 1]);
-            }
+          for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(v1[i]));
+          if (c + 2 < NCH) {
+            tmem_ld_x16(s_addr + (c + 2) * 16, v0);
           } else {
-            uint32_t pk[16];
-            const float2 ri2 = make_float2(r_i, r_i);
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              const float4 rj = *reinterpret_cast<const float4*>(rk + c * 32 + 2 * j);
-              const float2 p0 = __fmul2_rn(e[j], __fadd2_rn(ri2, make_float2(rj.x, rj.y)));
-              const float2 p1 = __fmul2_rn(e[j + 1], __fadd2_rn(ri2, make_float2(rj.z, rj.w)));
-              pk[j] = pack_bf16x2(p0.x, p0.y);
-              pk[j + 1] = pack_bf16x2(p1.x, p1.y);
+            if (!BWD) {  // every column of this S tile is in registers: hand the buffer back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_sm_done(buf));
             }
-            // P (bf16, 2 keys per column) overwrites S columns this warpgroup has already read:
-            // keys [half*64 + c*32, +32) -> columns half*64 + c*16 .. +16
-            tmem_st_x16(s_addr + c * 16, pk);
+            if (jj + 1 < n) {  // start on the next tile if its S (and r_j) are already there
+              const int buf_n = (NQ == 2) ? team * MODB + sb_n : sb_n;
+              bool ready = mbar_try_wait(bar_s_full(buf_n), sph_n) != 0;
+              if (BWD) ready = ready && mbar_try_wait(bar_k_full(kst_n), kph_n) != 0;
+              if (ready) {
+                tc_fence_after();
+                tmem_ld_x16(lane_base + buf_n * 128, v0);
+                have = true;
+              }
+            }
           }
+          CX_MARK(1);
+          if (POLY_A == POLY_B || !(wgi & 1))
+            softmax_chunk<BWD, POLY_A, DEG>(v1, s_addr + (c + 1) * 8, rk + (c + 1) * 16, cx, special,
+                                            kbase + (c + 1) * 16, acc_m, acc_p);
+          else
+            softmax_chunk<BWD, POLY_B, DEG>(v1, s_addr + (c + 1) * 8, rk + (c + 1) * 16, cx, special,
+                                            kbase + (c + 1) * 16, acc_m, acc_p);
         }
 
-        if (BWD) tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_sm_done(buf));
+        if (BWD) {
+          tc_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_sm_done(buf));
+        }
+        sb = sb_n;
+        sph = sph_n;
+        kst = kst_n;
+        kph = kph_n;
+        CX_MARK(3);
       }
 
       if (!BWD) {
-        if (valid) atomicAdd(p.l_out + row, (acc01.x + acc01.y) + (acc23.x + acc23.y));
+        if (valid) {
+          const float2 sm = __fadd2_rn(acc_m[0], acc_m[1]), sp = __fadd2_rn(acc_p[0], acc_p[1]);
+          atomicAdd(p.l_out + row, (sm.x + sm.y) + kscale * (sp.x + sp.y));
+        }
       } else {
         mbar_wait(bar_dz_full, useg & 1);
         tc_fence_after();
         // NQ == 2: team t owns accumulator t (D columns), its two warpgroups flush D/2 each;
         // NQ == 1: the four warpgroups share the single accumulator, max(D/4, 32) columns each
         constexpr int NCOL = (NQ == 2) ? D / 2 : (D / 4 >= 32 ? D / 4 : 32);
-        const int wg = team * 2 + half;
-        const int col0 = (NQ == 2) ? half * NCOL : wg * NCOL;
+        const int col0 = (NQ == 2) ? (wgi & 1) * NCOL : wgi * NCOL;
         const bool has_cols = col0 < D;
-        const uint32_t a_addr = lane_base + C::TMEM_DZ0 + ((NQ == 2) ? team * D : 0) + col0;
+        const uint32_t a_addr = tmem_base + (uint32_t(w4 * 32) << 16) + C::TMEM_DZ0 +
+                                ((NQ == 2) ? team * D : 0) + col0;
         if (has_cols) {
 #pragma unroll
           for (int c = 0; c < NCOL / 32; ++c) {
@@ -457,10 +645,14 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_dz_free);
       }
-      t += n;
+      CX_MARK(4);
       it += n;
       ++useg;
     }
+#if MAAI_PROF
+    if (lane == 0)
+      for (int i = 0; i < 8; ++i) g_prof[((size_t)blockIdx.x * 20 + warp) * 8 + i] = cx.prof_a[i];
+#endif
   }
 
   tc_fence_before();

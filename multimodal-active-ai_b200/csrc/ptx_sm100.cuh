@@ -200,6 +200,23 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
+      "r"(r[7])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -223,19 +240,30 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// exp2 on the FMA/ALU pipes for a pair of arguments in [-126, 1): Cody-Waite split with the
-// 1.5*2^23 magic number (t = x + magic rounds x to the nearest integer n in the low mantissa bits,
-// f = x - n in [-0.5, 0.5]), minimax polynomial for 2^f (max rel. error 7.5e-5 for degree 3,
-// 2.7e-6 for degree 4, fitted offline), exponent re-inserted by adding n << 23 to the bits of p.
-// This takes work off the 16-lane/clk MUFU unit, which is what bounds the softmax stage
-// (profiles/r1_ncu_summary_v1.md: XU pipe 77 % busy, FMA pipe 21 %).  Callers guarantee
-// x >= -126 (temperature >= 0.025 and |cos| <= 1 + bf16 rounding).
+// 2^(s*c) for a pair of dot products on the FMA/ALU pipes (no MUFU), |s*c| <= 126.
+// One FFMA2 forms t = s*c + 1.5*2^23, which rounds y = s*c to the nearest integer n in the low
+// mantissa bits; f = y - n in [-0.5, 0.5] comes from a second FFMA2 (single rounding of s*c - n);
+// a minimax polynomial gives 2^f (max rel. error 7.5e-5 for degree 3, 2.7e-6 for degree 4, fitted
+// offline) and one LEA per element adds n << 23 to the exponent field.  6 (degree 3) packed
+// FMA-pipe instructions + 2 ALU instructions per PAIR, against 1 FFMA2 + 2 MUFU.EX2 (8 clk each per
+// warp) on the MUFU path.  The caller folds the constant 2^(-c) of exp2(s*c - c) in afterwards.
+__device__ __forceinline__ float exp_insert(float p, float t) {
+  uint32_t r;
+  asm("{\n\t"
+      ".reg .b32 s;\n\t"
+      "shl.b32 s, %2, 23;\n\t"
+      "add.s32 %0, s, %1;\n\t"
+      "}"
+      : "=r"(r)
+      : "r"(__float_as_uint(p)), "r"(__float_as_uint(t)));
+  return __uint_as_float(r);
+}
 template <int DEG>
-__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+__device__ __forceinline__ float2 exp2_dot_poly2(float2 s, float2 c) {
   const float2 magic = make_float2(12582912.f, 12582912.f);
-  const float2 t = __fadd2_rn(x, magic);
-  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
-  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+  const float2 t = __ffma2_rn(s, c, magic);
+  const float2 nn = __fadd2_rn(make_float2(-t.x, -t.y), magic);  // -n, exact
+  const float2 f = __ffma2_rn(s, c, nn);
   float2 pl;
   if (DEG == 3) {
     pl = __ffma2_rn(f, make_float2(5.517165389e-02f, 5.517165389e-02f),
@@ -249,10 +277,7 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
     pl = __ffma2_rn(pl, f, make_float2(6.931218148e-01f, 6.931218148e-01f));
     pl = __ffma2_rn(pl, f, make_float2(9.999992614e-01f, 9.999992614e-01f));
   }
-  float2 r;
-  r.x = __int_as_float(__float_as_int(pl.x) + (__float_as_int(t.x) << 23));
-  r.y = __int_as_float(__float_as_int(pl.y) + (__float_as_int(t.y) << 23));
-  return r;
+  return make_float2(exp_insert(pl.x, t.x), exp_insert(pl.y, t.y));
 }
 
 // two fp32 -> packed bf16x2 (lo in bits [0,16), hi in bits [16,32)), round to nearest even

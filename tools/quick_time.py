@@ -12,7 +12,7 @@ from maai_b200.Objective import _Profiler  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 d = int(sys.argv[2]) if len(sys.argv) > 2 else 128
-iters = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 30
 tau = float(sys.argv[4]) if len(sys.argv) > 4 else 0.5
 g = torch.Generator(device="cuda").manual_seed(1234)
 x = torch.randn(B, d, generator=g, device="cuda").requires_grad_(True)
@@ -31,6 +31,6 @@ f = [a.elapsed_time(b) for a, b in _Profiler.events["fwd"]]
 w = [a.elapsed_time(b) for a, b in _Profiler.events["bwd"]]
 fm, wm = statistics.median(f), statistics.median(w)
 fl = 24.0 * B * B * d
-print(f"{os.path.basename(os.environ.get('MAAI_DEBUG_LIB', 'default')):28s} B={B} d={d} fwd {fm:.4f} ms  bwd {wm:.4f} ms  "
-      f"sum {fm + wm:.4f} ms -> {fl / ((fm + wm) * 1e-3) / 1e12:.1f} TFLOP/s alg  loss {float(loss.detach()):.6f} "
-      f"|dx| {float(x.grad.norm()):.6e}")
+print(f"{os.path.basename(os.environ.get('MAAI_DEBUG_LIB', 'default')):24s} B={B} d={d} fwd {fm:.4f} (min {min(f):.4f}) "
+      f"bwd {wm:.4f} (min {min(w):.4f}) sum {fm + wm:.4f} ms -> {fl / ((fm + wm) * 1e-3) / 1e12:.1f} TFLOP/s alg  "
+      f"loss {float(loss.detach()):.6f} |dx| {float(x.grad.norm()):.6e}")
