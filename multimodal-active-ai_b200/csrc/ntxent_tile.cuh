@@ -63,9 +63,24 @@
 #define MAAI_POLY_DEG_BWD 3
 #endif
 // Timing-only ablations (results are WRONG when non-zero; tools/ablate.py): bit 0 no exp,
-// bit 1 no P.Z MMAs, bit 2 no S MMAs, bit 3 no r_j loads.
+// bit 1 no P.Z MMAs, bit 2 no S MMAs, bit 3 no r_j loads, bit 4 no K-tile TMA traffic.
 #ifndef MAAI_ABL
 #define MAAI_ABL 0
+#endif
+// Columns per tcgen05.ld / register chunk of a softmax thread that owns 64 columns of an S tile:
+// 32 = one register buffer, load -> wait -> process (more independent work per chunk; measured
+// 3-5 % faster in both kernels), 16 = two buffers with the next load in flight and a cross-tile
+// prefetch behind a non-blocking barrier probe.
+#ifndef MAAI_FWD_CW
+#define MAAI_FWD_CW 32
+#endif
+#ifndef MAAI_BWD_CW
+#define MAAI_BWD_CW 32
+#endif
+// NQ == 1: 2 = the softmax warps form two teams of 8 that take alternate S tiles (64 columns per
+// thread), 1 = all 16 warps work on every S tile (32 columns per thread).
+#ifndef MAAI_NQ1_TEAMS
+#define MAAI_NQ1_TEAMS 2
 #endif
 
 // Per-warp phase timers (clock64) for tools/phase_prof.py; compiled out unless MAAI_PROF=1.
@@ -158,8 +173,13 @@ __device__ __forceinline__ void s_tile_slot(uint32_t sg, int& buf, uint32_t& pha
   }
 }
 
-// One 16-column chunk of one TMEM lane (= anchor row) of an S tile, already in registers: E -> row
-// sum (FWD) or P = E (r_i + r_j) -> bf16 -> tcgen05.st (BWD).  Of the 8 column pairs, POLY take the
+__device__ __forceinline__ void tmem_ld_cw(uint32_t a, uint32_t (&r)[16]) { tmem_ld_x16(a, r); }
+__device__ __forceinline__ void tmem_ld_cw(uint32_t a, uint32_t (&r)[32]) { tmem_ld_x32(a, r); }
+__device__ __forceinline__ void tmem_st_pk(uint32_t a, const uint32_t (&r)[8]) { tmem_st_x8(a, r); }
+__device__ __forceinline__ void tmem_st_pk(uint32_t a, const uint32_t (&r)[16]) { tmem_st_x16(a, r); }
+
+// One CW-column chunk of one TMEM lane (= anchor row) of an S tile, already in registers: E -> row
+// sum (FWD) or P = E (r_i + r_j) -> packed bf16 in pk (BWD; the caller stores it to TMEM).  Of the 8 column pairs, POLY take the
 // polynomial exp2 on the FMA pipe, the rest MUFU.EX2.  The polynomial path yields E * 2^c1 (see
 // exp2_dot_poly2); FWD keeps those in their own accumulators, BWD folds 2^-c1 into (r_i + r_j).
 struct ChunkCtx {
@@ -184,19 +204,20 @@ struct ChunkCtx {
 #else
 #define CX_MARK(i) do { } while (0)
 #endif
-template <bool BWD, int POLY, int DEG>
-__device__ __forceinline__ void softmax_chunk(uint32_t (&v)[16], uint32_t st_addr, const float* rk,
+template <bool BWD, int POLY, int DEG, int CW>
+__device__ __forceinline__ void softmax_chunk(uint32_t (&v)[CW], uint32_t (&pk)[CW / 2], const float* rk,
                                               ChunkCtx& cx, bool special, int kc0,
                                               float2 (&acc_m)[2], float2 (&acc_p)[2]) {
   // packed f32x2 math throughout (FFMA2 / FADD2 / FMUL2): half the FMA-pipe issue slots
   const float2 c1p = make_float2(cx.c1, cx.c1), c1n = make_float2(-cx.c1, -cx.c1);
-  float2 e[8];
+  constexpr int NP = CW / 2;  // column pairs
+  float2 e[NP];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < NP; ++j) {
     const float2 sv = make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
     if (MAAI_ABL & 1) {
       e[j] = __ffma2_rn(sv, c1p, c1n);
-    } else if (j < POLY) {
+    } else if ((j & 7) < POLY) {
       e[j] = exp2_dot_poly2<DEG>(sv, c1p);
     } else {
       const float2 x = __ffma2_rn(sv, c1p, c1n);
@@ -206,7 +227,7 @@ __device__ __forceinline__ void softmax_chunk(uint32_t (&v)[16], uint32_t st_add
   }
   if (special) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NP; ++j) {
       const int kc = kc0 + 2 * j;
       if (kc == cx.grow || kc == cx.gpos || kc >= cx.m_glob) e[j].x = 0.f;
       if (kc + 1 == cx.grow || kc + 1 == cx.gpos || kc + 1 >= cx.m_glob) e[j].y = 0.f;
@@ -214,28 +235,25 @@ __device__ __forceinline__ void softmax_chunk(uint32_t (&v)[16], uint32_t st_add
   }
   if (!BWD) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (j < POLY) acc_p[j & 1] = __fadd2_rn(acc_p[j & 1], e[j]);
+    for (int j = 0; j < NP; ++j) {
+      if ((j & 7) < POLY) acc_p[j & 1] = __fadd2_rn(acc_p[j & 1], e[j]);
       else acc_m[j & 1] = __fadd2_rn(acc_m[j & 1], e[j]);
     }
   } else {
-    uint32_t pk[8];
     const float2 ri2 = make_float2(cx.r_i, cx.r_i), rik2 = make_float2(cx.r_ik, cx.r_ik);
     const float2 ks2 = make_float2(cx.kscale, cx.kscale);
 #pragma unroll
-    for (int j = 0; j < 8; j += 2) {
+    for (int j = 0; j < NP; j += 2) {
       float4 rj = (MAAI_ABL & 8) ? make_float4(0.f, 0.f, 0.f, 0.f)
                                  : *reinterpret_cast<const float4*>(rk + 2 * j);
       const float2 rj0 = make_float2(rj.x, rj.y), rj1 = make_float2(rj.z, rj.w);
-      const float2 w0 = (j < POLY) ? __ffma2_rn(rj0, ks2, rik2) : __fadd2_rn(ri2, rj0);
-      const float2 w1 = (j + 1 < POLY) ? __ffma2_rn(rj1, ks2, rik2) : __fadd2_rn(ri2, rj1);
+      const float2 w0 = ((j & 7) < POLY) ? __ffma2_rn(rj0, ks2, rik2) : __fadd2_rn(ri2, rj0);
+      const float2 w1 = (((j + 1) & 7) < POLY) ? __ffma2_rn(rj1, ks2, rik2) : __fadd2_rn(ri2, rj1);
       const float2 p0 = __fmul2_rn(e[j], w0);
       const float2 p1 = __fmul2_rn(e[j + 1], w1);
       pk[j] = pack_bf16x2(p0.x, p0.y);
       pk[j + 1] = pack_bf16x2(p1.x, p1.y);
     }
-    // P (bf16, 2 keys per column) overwrites S columns this thread has already read
-    tmem_st_x8(st_addr, pk);
   }
   CX_MARK(2);
 }
@@ -284,7 +302,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
     }
     for (int u = 0; u < NB; ++u) {
       mbar_init(bar_s_full(u), 1);
-      mbar_init(bar_sm_done(u), NQ == 2 ? 8 : 16);  // one arrive per warp working on the tile
+      mbar_init(bar_sm_done(u), (NQ == 2 || MAAI_NQ1_TEAMS == 2) ? 8 : 16);  // one arrive per warp on the tile
     }
     mbar_init(bar_dz_full, 1);
     mbar_init(bar_dz_free, 16);      // one arrive per softmax warp
@@ -324,6 +342,10 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
           const int st = t % NST;
           mbar_wait(bar_k_empty(st), ((t / NST) & 1) ^ 1);
           PROF_MARK(1);
+          if ((MAAI_ABL & 16) && t >= NST) {  // timing ablation: no K / r_j traffic after the first ring fill
+            mbar_arrive(bar_k_full(st));
+            continue;
+          }
           mbar_arrive_expect_tx(bar_k_full(st), C::TILE_BYTES + (BWD ? C::KT * 4 : 0));
 #pragma unroll
           for (int c = 0; c < C::CHUNKS; ++c)
@@ -399,9 +421,10 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
         for (int k = 0; k < C::KT / 16; ++k) {
           // 16 keys = 16 smem rows of 128 B (2048 B).  P (2 keys per 32-bit column) of each
           // thread's key range sits at the start of that range's S columns:
-          // NQ == 2: 64 keys per warpgroup -> key half h at columns [h*64, h*64+32)
-          // NQ == 1: 32 keys per warpgroup -> key quarter c at columns [c*32, c*32+16)
-          const uint32_t pcol = (NQ == 2) ? (k >> 2) * 64 + (k & 3) * 8 : (k >> 1) * 32 + (k & 1) * 8;
+          // 64 keys per thread (two teams) -> key half h at columns [h*64, h*64+32)
+          // 32 keys per thread (one team)  -> key quarter c at columns [c*32, c*32+16)
+          const uint32_t pcol = (NQ == 2 || MAAI_NQ1_TEAMS == 2) ? (k >> 2) * 64 + (k & 3) * 8
+                                                                 : (k >> 1) * 32 + (k & 1) * 8;
           umma_ts(d_tmem, a_tmem + pcol, bd + k * (2048 >> 4), IDESC_PV,
                   (first && k == 0) ? 0u : 1u);
         }
@@ -471,11 +494,16 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // =========================== softmax warps ===========================
     const int sw = warp - 4;
     const int wgi = sw >> 2;                          // softmax warpgroup 0..3
-    const int team = (NQ == 2) ? (wgi >> 1) : 0;      // NQ == 2: Q tile owned by this warp
-    constexpr int TCOLS = (NQ == 2) ? 64 : 32;        // key columns per thread per S tile
-    constexpr int NCH = TCOLS / 16;                   // 16-column register chunks per S tile
+    constexpr int TEAMS = (NQ == 2) ? 2 : MAAI_NQ1_TEAMS;
+    // NQ == 2: team t owns Q tile t.  NQ == 1, two teams: team t takes the S tiles of parity t.
+    const int team = (TEAMS == 2) ? (wgi >> 1) : 0;
+    constexpr int STEP = (NQ == 1 && TEAMS == 2) ? 2 : 1;  // ring steps between tiles of this warp
+    constexpr int TCOLS = (TEAMS == 2) ? 64 : 32;     // key columns per thread per S tile
+    // columns per tcgen05.ld / register chunk
+    constexpr int CW = (TCOLS == 64) ? (BWD ? MAAI_BWD_CW : MAAI_FWD_CW) : 16;
+    constexpr int NCH = TCOLS / CW;                   // register chunks per S tile (even)
     constexpr int MODB = (NQ == 2) ? NB / 2 : NB;     // S buffers this warp cycles through
-    const int col_off = (NQ == 2) ? (wgi & 1) * 64 : wgi * 32;  // first key column of this thread
+    const int col_off = (TEAMS == 2) ? (wgi & 1) * 64 : wgi * 32;  // first key column of this thread
     const int w4 = warp & 3;          // TMEM lane quarter this warp may touch
     const int row_in_tile = w4 * 32 + lane;
     const uint32_t lane_base = tmem_base + (uint32_t(w4 * 32) << 16) + col_off;
@@ -488,10 +516,12 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // in the per-tile path): S buffer slot + phase, K stage + phase.
     int sb = 0, kst = 0;
     uint32_t sph = 0, kph = 0;
+    uint32_t tpar = 0;  // parity of the CTA-wide S-tile counter (NQ == 1, two teams)
     const int kt_ragged = (p.m_glob & (C::KT - 1)) ? p.nkt - 1 : -8;
     uint32_t useg = 0;
     // v0 holds (or is receiving) the first chunk of the next tile when `have` is set
-    uint32_t v0[16], v1[16];
+    MBAR_PROBE_DECL();
+    uint32_t v0[CW], v1[CW];
     bool have = false;
     ChunkCtx cx;
     cx.c1 = c1;
@@ -533,69 +563,97 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const uint32_t s_addr = lane_base + buf * 128;
         const float* rk = rk_gen + kst * C::KT + col_off;
         const int kbase = kt * C::KT + col_off;
+        if (STEP == 2 && int(tpar) != team) {  // the other team's tile: just step the rings
+          if (++sb == MODB) { sb = 0; sph ^= 1; }
+          if (++kst == NST) { kst = 0; kph ^= 1; }
+          tpar ^= 1;
+          continue;
+        }
         CX_MARK(5);
         if (!have) {
           if (BWD) mbar_wait(bar_k_full(kst), kph);  // r_j of this stage has landed
           mbar_wait(bar_s_full(buf), sph);
           tc_fence_after();
-          tmem_ld_x16(s_addr, v0);
+          tmem_ld_cw(s_addr, v0);
         }
         CX_MARK(0);
-        // ring positions of the tile after this one
+        // ring positions of the tile after this one; probe its barriers now (non-blocking), use
+        // the answer when the last chunk of this tile has been loaded
         int sb_n = sb + 1, kst_n = kst + 1;
         uint32_t sph_n = sph, kph_n = kph;
         if (sb_n == MODB) { sb_n = 0; sph_n ^= 1; }
         if (kst_n == NST) { kst_n = 0; kph_n ^= 1; }
+        // S buffer + phase of the next tile of THIS warp (two ring steps ahead with alternating teams)
+        int sb_p = sb_n;
+        uint32_t sph_p = sph_n;
+        if (STEP == 2 && ++sb_p == MODB) { sb_p = 0; sph_p ^= 1; }
+        const int buf_n = (NQ == 2) ? team * MODB + sb_p : sb_p;
+        // (no probe of the next K stage: its k_full phase completed before the MMA warp issued the
+        // S tile this probe is about, so the r_j values are in shared memory once s_full is)
+        const bool probe = CW == 16 && jj + STEP < n;
+        if (probe) mbar_probe_issue(bar_s_full(buf_n), sph_p);
         have = false;
 
         // Chunks are double-buffered in registers: the tcgen05.ld of chunk c + 1 (or of the next
         // tile's first chunk, if its S tile is already complete) is in flight while chunk c is
         // processed.  keys [col_off + c*16, +16) -> P columns col_off + c*8 .. +8.
+        auto process = [&](uint32_t (&v)[CW], int c) {
+          uint32_t pk[CW / 2];
+          if (POLY_A == POLY_B || !(wgi & 1))
+            softmax_chunk<BWD, POLY_A, DEG, CW>(v, pk, rk + c * CW, cx, special, kbase + c * CW, acc_m, acc_p);
+          else
+            softmax_chunk<BWD, POLY_B, DEG, CW>(v, pk, rk + c * CW, cx, special, kbase + c * CW, acc_m, acc_p);
+          // P (bf16, 2 keys per column) overwrites S columns this thread has already read
+          if (BWD) tmem_st_pk(s_addr + c * (CW / 2), pk);
+        };
+        if (CW == 32) {
+          // 32-column chunks, one register buffer (two would spill under the 96-register cap):
+          // load -> wait -> process, no cross-tile prefetch
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            if (c > 0) tmem_ld_cw(s_addr + c * CW, v0);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < CW; ++i) asm volatile("" : "+r"(v0[i]));
+            if (!BWD && c == NCH - 1) {  // every column of this S tile is in registers
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_sm_done(buf));
+            }
+            CX_MARK(1);
+            process(v0, c);
+          }
+        } else {
 #pragma unroll
         for (int c = 0; c < NCH; c += 2) {
           tc_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(v0[i]));
-          tmem_ld_x16(s_addr + (c + 1) * 16, v1);
+          for (int i = 0; i < CW; ++i) asm volatile("" : "+r"(v0[i]));
+          tmem_ld_cw(s_addr + (c + 1) * CW, v1);
           CX_MARK(1);
-          if (POLY_A == POLY_B || !(wgi & 1))
-            softmax_chunk<BWD, POLY_A, DEG>(v0, s_addr + c * 8, rk + c * 16, cx, special,
-                                            kbase + c * 16, acc_m, acc_p);
-          else
-            softmax_chunk<BWD, POLY_B, DEG>(v0, s_addr + c * 8, rk + c * 16, cx, special,
-                                            kbase + c * 16, acc_m, acc_p);
+          process(v0, c);
           tc_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(v1[i]));
+          for (int i = 0; i < CW; ++i) asm volatile("" : "+r"(v1[i]));
           if (c + 2 < NCH) {
-            tmem_ld_x16(s_addr + (c + 2) * 16, v0);
+            tmem_ld_cw(s_addr + (c + 2) * CW, v0);
           } else {
             if (!BWD) {  // every column of this S tile is in registers: hand the buffer back
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(bar_sm_done(buf));
             }
-            if (jj + 1 < n) {  // start on the next tile if its S (and r_j) are already there
-              const int buf_n = (NQ == 2) ? team * MODB + sb_n : sb_n;
-              bool ready = mbar_try_wait(bar_s_full(buf_n), sph_n) != 0;
-              if (BWD) ready = ready && mbar_try_wait(bar_k_full(kst_n), kph_n) != 0;
-              if (ready) {
-                tc_fence_after();
-                tmem_ld_x16(lane_base + buf_n * 128, v0);
-                have = true;
-              }
+            if (probe && mbar_probe_result()) {  // start on the next tile: its S is already there
+              tc_fence_after();
+              tmem_ld_cw(lane_base + buf_n * 128, v0);
+              have = true;
             }
           }
           CX_MARK(1);
-          if (POLY_A == POLY_B || !(wgi & 1))
-            softmax_chunk<BWD, POLY_A, DEG>(v1, s_addr + (c + 1) * 8, rk + (c + 1) * 16, cx, special,
-                                            kbase + (c + 1) * 16, acc_m, acc_p);
-          else
-            softmax_chunk<BWD, POLY_B, DEG>(v1, s_addr + (c + 1) * 8, rk + (c + 1) * 16, cx, special,
-                                            kbase + (c + 1) * 16, acc_m, acc_p);
+          process(v1, c + 1);
         }
-
-        if (BWD) {
+        }
+        if (BWD) {  // hand P over right away: the P.Z MMA and the next S tile queue behind it
           tc_wait_st();
           tc_fence_before();
           __syncwarp();
@@ -605,6 +663,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
         sph = sph_n;
         kst = kst_n;
         kph = kph_n;
+        tpar ^= 1;
         CX_MARK(3);
       }
 

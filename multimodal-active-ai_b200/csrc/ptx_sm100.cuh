@@ -44,6 +44,36 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// Non-blocking probe (try_wait may suspend the thread for a while; test_wait never does)
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Split probe: MBAR_PROBE_DECL() once at function scope declares a PTX predicate; mbar_probe_issue()
+// starts a non-blocking test_wait into it and mbar_probe_result() reads it later.  Unlike the
+// one-statement form above, nothing consumes the predicate right behind the SYNCS instruction, so
+// its ~150 clk latency overlaps whatever the caller puts in between (in-order issue would
+// otherwise stall on the selp).  One probe may be outstanding per thread.
+#define MBAR_PROBE_DECL() asm volatile(".reg .pred maai_probe_p;")
+__device__ __forceinline__ void mbar_probe_issue(uint32_t bar, uint32_t parity) {
+  asm volatile("mbarrier.test_wait.parity.shared::cta.b64 maai_probe_p, [%0], %1;" ::"r"(bar),
+               "r"(parity)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_probe_result() {
+  uint32_t ok;
+  asm volatile("selp.u32 %0, 1, 0, maai_probe_p;" : "=r"(ok)::"memory");
+  return ok;
+}
 // Bounded wait: a pipeline bug must trap (-> CUDA error surfaced through the C ABI), never hang
 // the GPU.  ~4e9 SM cycles is > 2 s at any clock; a healthy wait is microseconds.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {

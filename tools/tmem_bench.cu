@@ -56,6 +56,42 @@ __global__ void __launch_bounds__(640, 1) bench(Args a) {
     // groups of 8 tiles; one group stays in flight while the previous one is waited for
     for (int it = 0; it < a.mma_iters; ++it) {
       constexpr int m = MM;
+      if (m >= 9) {  // straight-line pairs of tiles: it even -> first kind (8 MMAs), it odd -> second kind
+        if (it & 1) continue;
+        if (elect_one()) {
+          const uint32_t d0 = tmem + 256, d1 = tmem + 384;
+          auto first = [&](uint32_t d) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t off = ((k >> 2) * 16384 + (k & 3) * 32) >> 4;
+              if (m == 11) umma_ts(d, tmem + 128 + k * 8, dk + (sA >> 4) + off, IDESC, k > 0);
+              else umma_ss(d, dk + (sA >> 4) + off, dk + (sB >> 4) + off, IDESC, k > 0);
+            }
+          };
+          auto second = [&](uint32_t d) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t off = ((k >> 2) * 16384 + (k & 3) * 32) >> 4;
+              if (m == 12) umma_ss(d, dk + (sA >> 4) + off, dmn + (sB >> 4) + k * 128, IDESC_PV, k > 0);
+              else if (m == 13) umma_ss(d, dk + (sA >> 4) + off, dk + (sB >> 4) + off, IDESC, k > 0);
+              else umma_ts(d, tmem + 128 + k * 8, dmn + (sB >> 4) + k * 128, IDESC_PV, k > 0);
+            }
+          };
+          if (m == 10) {  // SS, SS, TS, TS
+            if (it & 2) { second(d1); second(d1); } else { first(d0); first(d0); }
+          } else {
+            first(d0);
+            second(d1);
+          }
+          if ((it & 7) == 6) umma_commit(bar + 8 * ((it >> 3) & 1));
+        }
+        __syncwarp();
+        if ((it & 7) == 6 && it >= 14) {
+          const int g = (it >> 3) - 1;
+          mbar_wait(bar + 8 * (g & 1), (g >> 1) & 1);
+        }
+        continue;
+      }
       const bool wide = (m == 4 || m == 6 || m == 7);
       const uint32_t d = wide ? tmem + 256 : tmem + 256 + (it & 1) * 128;
       const bool ts = m == 2 || (m == 3 && (it & 1));
@@ -152,7 +188,7 @@ int main() {
   long long* out;
   cudaMalloc(&out, sizeof(long long) * 2 * sms);
   const int smem = 65536 + 2048;
-#define FOR_MODES(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+#define FOR_MODES(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13)
 #define SETATTR(M) cudaFuncSetAttribute(bench<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   FOR_MODES(SETATTR)
   auto run = [&](const char* name, int ld_warps, int ld_mode, int ld_iters, int mma_mode, int mma_iters, int same) {
@@ -195,6 +231,12 @@ int main() {
     run("mma TS K-major B N=256 (per 2 tiles)", 0, 0, 0, 6, N, 0);
     run("mma TS MN-major B N=256 (per 2 tiles)", 0, 0, 0, 7, N, 0);
     run("mma SS N=64 (per half tile)", 0, 0, 0, 8, N, 0);
+    run("mma alt SS / TS(MN) (branch, unpredicated)", 0, 0, 0, 9, N, 0);
+    run("mma alt SS,SS / TS,TS", 0, 0, 0, 10, N, 0);
+    run("mma alt TS(K-major) / TS(MN-major)", 0, 0, 0, 11, N, 0);
+    run("mma alt SS(K) / SS(MN-major B)", 0, 0, 0, 12, N, 0);
+    run("mma alt SS(D0) / SS(D1) control", 0, 0, 0, 13, N, 0);
+    run("alt SS/TS + ld x32 + st x16 16 warps (N/2)", 16, 4, N / 2, 9, N, 0);
     run("mma SS + ld 4 warps (N tiles each)", 4, 1, N, 1, N, 0);
     run("mma SS + ld 16 warps (N/4 tiles per wg)", 16, 1, N / 4, 1, N, 0);
     run("mma SS + ld 16 warps (N/2 tiles per wg)", 16, 1, N / 2, 1, N, 0);
