@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MAAI_ABI_VERSION 1
+#define MAAI_ABI_VERSION 2
 
 #define MAAI_OK 0
 #define MAAI_E_ARG (-1)
@@ -68,6 +68,17 @@ int maai_ntxent_normalize(const void* h1, const void* h2, int b, int d, int in_d
 int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
                     const float* pos_cos, float* rowsum_l, float* r_out, float* loss_out,
                     void* stream);
+
+/* K2 for validate() (Contrastive_Learning.py:860-868): the same forward plus, for every view-a anchor
+ * k of this rank, pos_rank[k] = number of view-b keys of ALL ranks whose similarity to the anchor is
+ * strictly greater than its positive's, i.e. the 0-based rank of the positive inside the row of
+ * logits_ab (Objective.py:73).  top-k accuracy (Model_Util.py:104-113) = mean(pos_rank < k): neither
+ * the (b, B) logits nor the (b, 2B) one-hot labels are materialised.  Exact ties count for the
+ * positive (torch.topk breaks ties arbitrarily).
+ *   pos_rank   (b) int32 out (zeroed inside) */
+int maai_ntxent_fwd_eval(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
+                         const float* pos_cos, float* rowsum_l, float* loss_out, int* pos_rank,
+                         void* stream);
 
 /* K3 + K4 -- replaces loss.backward() through Objective.py:41-79 (Contrastive_Learning.py:698).
  *   dZ_i = (1/tau) [ sum_{j != pos(i)} E_ij (r_row_i + r_col_j) z_j + cpos_i z_pos(i) ]   (i: this rank's anchors)

@@ -179,6 +179,30 @@ class _NTXentFunction(torch.autograd.Function):
         return dh1, dh2, None, None, None, None, None, None
 
 
+def _forward_eval(hidden1, hidden2, temperature, rank, world, group):
+    """validate() path without logits: loss + rank of every positive among the view-b keys
+    (maai_ntxent_fwd_eval).  No autograd graph."""
+    lib = _lib.load()
+    b, d = hidden1.shape
+    dev = hidden1.device
+    dp = padded_dim(d)
+    h1 = hidden1.detach().contiguous()
+    h2 = hidden2.detach().contiguous()
+    z_all = torch.empty((world, 2 * b, dp), dtype=torch.bfloat16, device=dev)
+    inv_norm = torch.empty(2 * b, dtype=torch.float32, device=dev)
+    pos_cos = torch.empty(b, dtype=torch.float32, device=dev)
+    rowsum = torch.empty(2 * b, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    ranks = torch.empty(b, dtype=torch.int32, device=dev)
+    _lib.check(lib.maai_ntxent_normalize(_ptr(h1), _ptr(h2), b, d, _DTYPES[h1.dtype], _ptr(z_all[rank]),
+                                         _ptr(inv_norm), _ptr(pos_cos), _stream()), "maai_ntxent_normalize")
+    gather_rows(z_all, rank, group)
+    _lib.check(lib.maai_ntxent_fwd_eval(_ptr(z_all), b, world, rank, dp, 1.0 / float(temperature),
+                                        _ptr(pos_cos), _ptr(rowsum), _ptr(loss), _ptr(ranks), _stream()),
+               "maai_ntxent_fwd_eval")
+    return loss, ranks
+
+
 def _validate(hidden1, hidden2, hidden_norm, temperature, world_size, local_rank):
     if hidden1.shape != hidden2.shape:
         raise AssertionError(f"hidden1.shape {tuple(hidden1.shape)} != hidden2.shape "
@@ -203,7 +227,8 @@ def _validate(hidden1, hidden2, hidden_norm, temperature, world_size, local_rank
 
 
 def contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0, local_rank=0, world_size=1,
-                     device="cpu", *, group=None, key_grad=True, return_logits=None, _stash=None):
+                     device="cpu", *, group=None, key_grad=True, return_logits=None, fused_topk=False,
+                     _stash=None):
     """Drop-in for Objective.contrastive_loss (Objective.py:17-81).
 
     Args (reference): hidden1, hidden2 (bsz, dim); hidden_norm; temperature; local_rank (really the
@@ -212,9 +237,23 @@ def contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0, local_
       ``return_logits`` force (True) / suppress (False) the (logits_ab, labels) outputs, default:
       only when autograd is disabled (the validate() path).
 
+      ``fused_topk=True`` (evaluation only: autograd disabled or no input requires grad): the second
+      return value is the int32 vector ``pos_rank`` (bsz,) -- how many view-b keys of all ranks are
+      more similar to each view-a anchor than its positive -- instead of the (bsz, B) logits, the
+      third is None; ``Model_Util.top_k_accuracy(pos_rank, None, k)`` of this package turns it into
+      the reference's contrastive top-k accuracy (Contrastive_Learning.py:867-868) without the
+      (bsz, B) fp32 logits and (bsz, 2B) int64 one-hot labels ever existing.
+
     Returns (loss, logits_ab, labels) like the reference.
     """
     _validate(hidden1, hidden2, hidden_norm, temperature, world_size, local_rank)
+    if fused_topk:
+        if torch.is_grad_enabled() and (hidden1.requires_grad or hidden2.requires_grad):
+            raise ValueError("fused_topk=True is the validate() path: call it under torch.no_grad() "
+                             "or with inputs that do not require grad")
+        loss, ranks = _forward_eval(hidden1, hidden2, float(temperature), int(local_rank),
+                                    int(world_size), group)
+        return loss, ranks, None
     stash = _stash
     want_logits = (not torch.is_grad_enabled()) if return_logits is None else bool(return_logits)
     if want_logits and stash is None:

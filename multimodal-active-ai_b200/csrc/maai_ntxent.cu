@@ -79,15 +79,20 @@ int sm_count() {
   return n;
 }
 
-template <int D, bool BWD, int NQ>
+struct RankArgs {
+  const float* pos_cos = nullptr;
+  int* rank_out = nullptr;
+};
+
+template <int D, bool BWD, int NQ, bool RANK = false>
 int launch_tile(const void* q_base, int m_loc, const void* k_base, int m_glob, int row_global_base,
                 float inv_tau, const float* r_row, const float* r_col, float* l_out, float* dz_acc,
-                int pos_split, int pos_delta, cudaStream_t s) {
+                int pos_split, int pos_delta, cudaStream_t s, RankArgs ra = RankArgs()) {
   using C = maai::TileCfg<D, BWD, NQ>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(maai::ntxent_tile_kernel<D, BWD, NQ>,
+    attr_err = cudaFuncSetAttribute(maai::ntxent_tile_kernel<D, BWD, NQ, RANK>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(smem)", attr_err);
@@ -108,6 +113,8 @@ int launch_tile(const void* q_base, int m_loc, const void* k_base, int m_glob, i
   p.r_col = r_col;
   p.l_out = l_out;
   p.dz_acc = dz_acc;
+  p.pos_cos = ra.pos_cos;
+  p.rank_out = ra.rank_out;
   // MN-major SW128 operand: LBO = distance between 64-column chunks, SBO = between 8-row groups
   static const uint32_t pv_lbo = getenv("MAAI_DEBUG_PV_LBO") ? atoi(getenv("MAAI_DEBUG_PV_LBO")) : C::CHUNK_BYTES;
   static const uint32_t pv_sbo = getenv("MAAI_DEBUG_PV_SBO") ? atoi(getenv("MAAI_DEBUG_PV_SBO")) : 1024;
@@ -117,7 +124,7 @@ int launch_tile(const void* q_base, int m_loc, const void* k_base, int m_glob, i
   int sms = sm_count();
   if (sms <= 0) return fail(MAAI_E_CUDA, "no CUDA device");
   const int grid = (int)(items < sms ? items : sms);
-  maai::ntxent_tile_kernel<D, BWD, NQ><<<grid, C::NTHREADS, C::SMEM_BYTES, s>>>(tq, tk, p);
+  maai::ntxent_tile_kernel<D, BWD, NQ, RANK><<<grid, C::NTHREADS, C::SMEM_BYTES, s>>>(tq, tk, p);
   ++g_launches;
   MAAI_CUDA(cudaGetLastError());
   return MAAI_OK;
@@ -214,9 +221,9 @@ int maai_ntxent_normalize(const void* h1, const void* h2, int b, int d, int in_d
   return MAAI_OK;
 }
 
-int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
+static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
                     const float* pos_cos, float* rowsum_l, float* r_out, float* loss_out,
-                    void* stream) {
+                    int* pos_rank, void* stream) {
   if (!z_glob || !pos_cos || !rowsum_l || !loss_out) return fail(MAAI_E_ARG, "null pointer");
   int rc = check_common(b, world, rank);
   if (rc != MAAI_OK) return rc;
@@ -226,13 +233,47 @@ int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, f
   const int m_loc = 2 * b, m_glob = 2 * b * world;
   MAAI_CUDA(cudaMemsetAsync(rowsum_l, 0, sizeof(float) * m_loc, s));
   const char* q_base = static_cast<const char*>(z_glob) + (size_t)rank * m_loc * d_pad * 2;
-  rc = dispatch_tile<false>(d_pad, q_base, m_loc, z_glob, m_glob, rank * m_loc, inv_tau, nullptr,
-                            nullptr, rowsum_l, nullptr, b, b, s);
+  if (pos_rank) {
+    // evaluation forward: same kernel + the rank of every view-a anchor's positive among the
+    // view-b keys (one instantiation per padded width, the forward's default tile layout)
+    MAAI_CUDA(cudaMemsetAsync(pos_rank, 0, sizeof(int) * b, s));
+    RankArgs ra;
+    ra.pos_cos = pos_cos;
+    ra.rank_out = pos_rank;
+#define MAAI_LAUNCH_RANK(DD, NQQ)                                                                   \
+  rc = launch_tile<DD, false, NQQ, true>(q_base, m_loc, z_glob, m_glob, rank * m_loc, inv_tau, nullptr, \
+                                         nullptr, rowsum_l, nullptr, b, b, s, ra)
+    switch (d_pad) {
+      case 64: MAAI_LAUNCH_RANK(64, 2); break;
+      case 128: MAAI_LAUNCH_RANK(128, 2); break;
+      case 256: MAAI_LAUNCH_RANK(256, 1); break;
+      default: return fail(MAAI_E_SHAPE, "d_pad must be 64, 128 or 256");
+    }
+#undef MAAI_LAUNCH_RANK
+  } else {
+    rc = dispatch_tile<false>(d_pad, q_base, m_loc, z_glob, m_glob, rank * m_loc, inv_tau, nullptr,
+                              nullptr, rowsum_l, nullptr, b, b, s);
+  }
   if (rc != MAAI_OK) return rc;
-  maai::finalize_loss_kernel<<<1, 1024, 0, s>>>(rowsum_l, pos_cos, b, inv_tau, r_out, loss_out);
+  maai::finalize_loss_kernel<<<maai::kFinalizeCluster, 1024, 0, s>>>(rowsum_l, pos_cos, b, inv_tau, r_out, loss_out);
   ++g_launches;
   MAAI_CUDA(cudaGetLastError());
   return MAAI_OK;
+}
+
+int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
+                    const float* pos_cos, float* rowsum_l, float* r_out, float* loss_out,
+                    void* stream) {
+  return fwd_impl(z_glob, b, world, rank, d_pad, inv_tau, pos_cos, rowsum_l, r_out, loss_out, nullptr,
+                  stream);
+}
+
+int maai_ntxent_fwd_eval(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
+                         const float* pos_cos, float* rowsum_l, float* loss_out, int* pos_rank,
+                         void* stream) {
+  if (!pos_rank) return fail(MAAI_E_ARG, "null pointer");
+  return fwd_impl(z_glob, b, world, rank, d_pad, inv_tau, pos_cos, rowsum_l, nullptr, loss_out, pos_rank,
+                  stream);
 }
 
 int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, int key_grad,

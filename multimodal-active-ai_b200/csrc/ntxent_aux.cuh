@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cooperative_groups.h>
 #include "ptx_sm100.cuh"
 
 namespace maai {
@@ -73,18 +74,26 @@ normalize_cast_kernel(const T* __restrict__ h1, const T* __restrict__ h2, int b,
   }
 }
 
-// Single block, deterministic.  With e_pos = exp((cos_pos - 1)/tau) and l' = sum over negatives:
+// One thread-block cluster of 8 CTAs (8192 threads), deterministic: fixed thread-strided partial
+// sums in fp64, one value per CTA written into CTA 0's shared memory over DSMEM, summed in rank
+// order.  (A single 1024-thread block took 45 us at 65536 rows, 1.7 % of the step.)
+// With e_pos = exp((cos_pos - 1)/tau) and l' = sum over negatives:
 //   lse_i - s_i,pos = ln(e_pos + l'_i) - ln(e_pos) = log1p(l'_i / e_pos)      (Objective.py:76-77)
 //   loss = (1/b) * sum_{i < 2b} log1p(l'_i / e_pos(i))                          (Objective.py:79)
 // and r_i = 1 / (b * (e_pos + l'_i)) for the backward.  r_out may be null.
-__global__ void __launch_bounds__(1024)
+constexpr int kFinalizeCluster = 8;
+__global__ void __cluster_dims__(kFinalizeCluster, 1, 1) __launch_bounds__(1024)
 finalize_loss_kernel(const float* __restrict__ l, const float* __restrict__ pos_cos, int b,
                      float inv_tau, float* __restrict__ r_out, float* __restrict__ loss_out) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ double part[32];
+  __shared__ double cta_part[kFinalizeCluster];  // CTA 0's copy collects one value per CTA
+  const unsigned rank = cluster.block_rank();
   double acc = 0.0;
   const float inv_b = 1.f / float(b);
   const float c1 = inv_tau * 1.4426950408889634f;
-  for (int i = threadIdx.x; i < 2 * b; i += blockDim.x) {
+  for (int i = rank * blockDim.x + threadIdx.x; i < 2 * b; i += kFinalizeCluster * blockDim.x) {
     const float ln = l[i];
     const float ep = ex2_approx(fmaf(pos_cos[i < b ? i : i - b], c1, -c1));
     acc += double(log1pf(ln / ep));
@@ -98,7 +107,14 @@ finalize_loss_kernel(const float* __restrict__ l, const float* __restrict__ pos_
     double v = (threadIdx.x < (blockDim.x >> 5)) ? part[threadIdx.x] : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0) *loss_out = float(v * double(inv_b));
+    if (threadIdx.x == 0) cluster.map_shared_rank(cta_part, 0)[rank] = v;
+  }
+  cluster.sync();
+  if (rank == 0 && threadIdx.x == 0) {
+    double v = 0.0;
+#pragma unroll
+    for (int r = 0; r < kFinalizeCluster; ++r) v += cta_part[r];
+    *loss_out = float(v * double(inv_b));
   }
 }
 

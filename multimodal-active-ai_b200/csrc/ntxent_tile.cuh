@@ -128,6 +128,10 @@ struct TileParams {
   float* dz_acc;         // BWD: m_loc x D fp32, pre-zeroed
   uint32_t pv_lbo;       // BWD: leading / stride byte offsets of the MN-major Z_J operand
   uint32_t pv_sbo;
+  // RANK (evaluation forward): for every view-a anchor, how many view-b keys are strictly more
+  // similar than its positive (contrastive top-k without logits, Model_Util.py:104-113)
+  const float* pos_cos;  // positive cosine per local pair (pos_split floats)
+  int* rank_out;         // pos_split ints, pre-zeroed
 };
 
 template <int D, bool BWD, int NQ>
@@ -189,6 +193,9 @@ struct ChunkCtx {
   float r_ik;      // BWD: r_i * 2^-c1
   int grow, gpos;  // key indices of this anchor's diagonal / positive entry
   int m_glob;
+  float pos_s;     // RANK: similarity of the positive (+inf for rows that are not counted)
+  int cnt;         // RANK: view-b keys more similar than the positive so far
+  int pairs;       // RANK: b (keys k with (k mod 2b) >= b belong to view b)
 #if MAAI_PROF
   long long prof_t;
   long long prof_a[8];
@@ -204,10 +211,25 @@ struct ChunkCtx {
 #else
 #define CX_MARK(i) do { } while (0)
 #endif
-template <bool BWD, int POLY, int DEG, int CW>
+template <bool BWD, int POLY, int DEG, int CW, bool RANK = false>
 __device__ __forceinline__ void softmax_chunk(uint32_t (&v)[CW], uint32_t (&pk)[CW / 2], const float* rk,
                                               ChunkCtx& cx, bool special, int kc0,
-                                              float2 (&acc_m)[2], float2 (&acc_p)[2]) {
+                                              float2 (&acc_m)[2], float2 (&acc_p)[2], int cmode = 0) {
+  if (RANK && cmode != 0) {
+    // cmode 1: every key of this tile is a view-b key and none needs a predicate; 2: test each key
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < CW; ++i) {
+      bool hit = __uint_as_float(v[i]) > cx.pos_s;
+      if (cmode == 2) {
+        const int kc = kc0 + i;
+        hit = hit && kc != cx.gpos && kc < cx.m_glob &&
+              (unsigned(kc) % unsigned(2 * cx.pairs)) >= unsigned(cx.pairs);
+      }
+      c += hit ? 1 : 0;
+    }
+    cx.cnt += c;
+  }
   // packed f32x2 math throughout (FFMA2 / FADD2 / FMUL2): half the FMA-pipe issue slots
   const float2 c1p = make_float2(cx.c1, cx.c1), c1n = make_float2(-cx.c1, -cx.c1);
   constexpr int NP = CW / 2;  // column pairs
@@ -258,7 +280,7 @@ __device__ __forceinline__ void softmax_chunk(uint32_t (&v)[CW], uint32_t (&pk)[
   CX_MARK(2);
 }
 
-template <int D, bool BWD, int NQ>
+template <int D, bool BWD, int NQ, bool RANK = false>
 __global__ void __launch_bounds__(640, 1)
 ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
                    const __grid_constant__ CUtensorMap tmap_k, const TileParams p) {
@@ -551,6 +573,12 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       cx.r_ik = cx.r_i * kscale;
       cx.grow = grow;
       cx.gpos = gpos;
+      if (RANK) {
+        const bool counted = !BWD && valid && row < p.pos_split;  // view-a anchors only
+        cx.pos_s = counted ? __ldg(p.pos_cos + row) : __int_as_float(0x7f800000);
+        cx.cnt = 0;
+        cx.pairs = p.pos_delta;
+      }
       float2 acc_m[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       float2 acc_p[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 
@@ -560,6 +588,11 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const int buf = (NQ == 2) ? team * MODB + sb : sb;
         const bool special = unsigned(kt - kt_d) <= 1u || unsigned(kt - kt_p1) <= 1u ||
                              unsigned(kt - kt_p2) <= 1u || kt == kt_ragged;
+        int cmode = 0;
+        if (RANK) {  // which keys of this tile are view-b keys: none / all / mixed
+          const int seg_lo = (kt * C::KT) / p.pos_delta, seg_hi = (kt * C::KT + C::KT - 1) / p.pos_delta;
+          cmode = (seg_lo != seg_hi || special) ? 2 : ((seg_lo & 1) ? 1 : 0);
+        }
         const uint32_t s_addr = lane_base + buf * 128;
         const float* rk = rk_gen + kst * C::KT + col_off;
         const int kbase = kt * C::KT + col_off;
@@ -600,9 +633,11 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
         auto process = [&](uint32_t (&v)[CW], int c) {
           uint32_t pk[CW / 2];
           if (POLY_A == POLY_B || !(wgi & 1))
-            softmax_chunk<BWD, POLY_A, DEG, CW>(v, pk, rk + c * CW, cx, special, kbase + c * CW, acc_m, acc_p);
+            softmax_chunk<BWD, POLY_A, DEG, CW, RANK>(v, pk, rk + c * CW, cx, special, kbase + c * CW,
+                                                      acc_m, acc_p, cmode);
           else
-            softmax_chunk<BWD, POLY_B, DEG, CW>(v, pk, rk + c * CW, cx, special, kbase + c * CW, acc_m, acc_p);
+            softmax_chunk<BWD, POLY_B, DEG, CW, RANK>(v, pk, rk + c * CW, cx, special, kbase + c * CW,
+                                                      acc_m, acc_p, cmode);
           // P (bf16, 2 keys per column) overwrites S columns this thread has already read
           if (BWD) tmem_st_pk(s_addr + c * (CW / 2), pk);
         };
@@ -671,6 +706,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (valid) {
           const float2 sm = __fadd2_rn(acc_m[0], acc_m[1]), sp = __fadd2_rn(acc_p[0], acc_p[1]);
           atomicAdd(p.l_out + row, (sm.x + sm.y) + kscale * (sp.x + sp.y));
+          if (RANK && row < p.pos_split && cx.cnt) atomicAdd(p.rank_out + row, cx.cnt);
         }
       } else {
         mbar_wait(bar_dz_full, useg & 1);

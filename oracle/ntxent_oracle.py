@@ -205,3 +205,26 @@ def contrastive_topk_oracle(hidden1, hidden2, k, hidden_norm=True):
     pos = np.diag(ab)
     rank_of_pos = (ab > pos[:, None]).sum(axis=1)
     return float((rank_of_pos < k).mean())
+
+
+def positive_rank_oracle(h1_ranks, h2_ranks, hidden_norm=True):
+    """Per rank p: for every local view-a anchor r, how many of the GLOBAL view-b keys are strictly
+    more similar than its positive -- the 0-based rank of column p*b + r inside row r of logits_ab
+    (Objective.py:73 with the cross-replica keys of :52-53; labels_idx + rank*b of :55).
+    top_k_accuracy(logits_ab, labels, k) (Model_Util.py:104-113) == mean(rank < k) barring exact ties.
+    Returns a list of int64 arrays (b,), one per rank."""
+    h1 = [np.asarray(h, np.float64) for h in h1_ranks]
+    h2 = [np.asarray(h, np.float64) for h in h2_ranks]
+    if hidden_norm:
+        h1 = [l2_normalise(h)[0] for h in h1]
+        h2 = [l2_normalise(h)[0] for h in h2]
+    z2_all = np.concatenate(h2, axis=0)
+    out = []
+    off = 0
+    for z1 in h1:
+        ab = z1 @ z2_all.T
+        b = z1.shape[0]
+        pos = ab[np.arange(b), off + np.arange(b)]
+        out.append((ab > pos[:, None]).sum(axis=1).astype(np.int64))
+        off += b
+    return out

@@ -70,6 +70,42 @@ def test_emulated_ranks_one_gpu(world, b, d, tau):
             assert rel_fro(g2.cpu().numpy(), r2[p]) <= 1e-2, (p, key_grad)
 
 
+@pytest.mark.parametrize("world,b,d", [(2, 96, 128), (4, 200, 64), (3, 130, 256), (8, 64, 128)])
+def test_emulated_ranks_fused_topk(world, b, d):
+    """maai_ntxent_fwd_eval with world > 1: rank p's pos_rank counts the view-b keys of ALL ranks
+    (column rank*b + k of logits_ab, Objective.py:55,73) -- vs the fp64 oracle."""
+    from maai_b200 import _lib
+    from oracle import ntxent_oracle as O
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(7 * world + b)
+    H1 = torch.randn(world * b, d, generator=g)
+    H2 = H1 + 0.9 * torch.randn(world * b, d, generator=g)
+    h1r = [H1[p * b:(p + 1) * b].contiguous() for p in range(world)]
+    h2r = [H2[p * b:(p + 1) * b].contiguous() for p in range(world)]
+    dp = lib.maai_padded_dim(d)
+    z_all = torch.zeros(world, 2 * b, dp, dtype=torch.bfloat16, device=dev)
+    inv = torch.zeros(world, 2 * b, device=dev)
+    cos = torch.zeros(world, b, device=dev)
+    for p in range(world):
+        a, c = h1r[p].to(dev), h2r[p].to(dev)
+        _lib.check(lib.maai_ntxent_normalize(a.data_ptr(), c.data_ptr(), b, d, 0, z_all[p].data_ptr(),
+                                             inv[p].data_ptr(), cos[p].data_ptr(), s), "k1")
+    ref = O.positive_rank_oracle([h.numpy() for h in h1r], [h.numpy() for h in h2r])
+    ol, _, _ = O.contrastive_loss_oracle_distributed([h.numpy() for h in h1r], [h.numpy() for h in h2r], 0.5, key_grad=False)
+    for p in range(world):
+        rowsum = torch.zeros(2 * b, device=dev)
+        loss = torch.zeros((), device=dev)
+        ranks = torch.full((b,), -1, dtype=torch.int32, device=dev)
+        _lib.check(lib.maai_ntxent_fwd_eval(z_all.data_ptr(), b, world, p, dp, 2.0, cos[p].data_ptr(),
+                                            rowsum.data_ptr(), loss.data_ptr(), ranks.data_ptr(), s), "eval")
+        torch.cuda.synchronize()
+        got = ranks.cpu().numpy()
+        assert abs(float(loss) - ol[p]) <= 1e-3 * abs(ol[p])
+        assert np.mean(np.abs(got - ref[p]) <= 1) > 0.9 and np.abs(got - ref[p]).max() <= max(3, 0.02 * b * world), p
+
+
 def test_two_gpu_torchrun(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")

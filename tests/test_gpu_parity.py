@@ -24,7 +24,7 @@ def _run(h1, h2, tau, need1=True, need2=True, dtype=torch.float32, **kw):
     loss, logits, labels = maai_b200.contrastive_loss(x, y, temperature=tau, device="cuda", **kw)
     loss.backward()
     torch.cuda.synchronize()
-    return (float(loss), None if x.grad is None else x.grad.float().cpu().numpy(),
+    return (float(loss.detach()), None if x.grad is None else x.grad.float().cpu().numpy(),
             None if y.grad is None else y.grad.float().cpu().numpy())
 
 
@@ -173,3 +173,60 @@ def test_validate_path_returns_logits_and_labels(golden):
     # training path does not materialise them
     x = h1.clone().requires_grad_(True)
     assert maai_b200.contrastive_loss(x, h2, temperature=1.0)[1] is None
+
+
+def _ranks_from_bf16_rows(z_all, b, rank, world):
+    """numpy restatement on the SAME bf16 rows the kernel multiplies (fp64 accumulate)."""
+    z = z_all.float().cpu().double().numpy()
+    z1 = z[rank, :b]
+    z2 = z[:, b:].reshape(world * b, -1)
+    ab = z1 @ z2.T
+    pos = ab[np.arange(b), rank * b + np.arange(b)]
+    return (ab > pos[:, None]).sum(1), ab, pos
+
+
+@pytest.mark.parametrize("b,d,tau,aligned", [(100, 64, 0.1, True), (256, 128, 0.5, False), (1000, 128, 0.5, True),
+                                              (37, 20, 0.5, False), (300, 256, 0.2, True), (4096, 128, 0.5, True)])
+def test_fused_topk_ranks(b, d, tau, aligned):
+    """validate() without logits: pos_rank from the evaluation forward vs the fp64
+    oracle (positive_rank_oracle, Model_Util.py:104-113 restated) and vs the logits path."""
+    import maai_b200
+    from oracle import ntxent_oracle as O
+    g = torch.Generator().manual_seed(b + d)
+    h1 = torch.randn(b, d, generator=g)
+    h2 = h1 + 0.8 * torch.randn(b, d, generator=g) if aligned else torch.randn(b, d, generator=g)
+    x, y = h1.cuda(), h2.cuda()
+    stash = {}
+    with torch.no_grad():
+        loss_f, ranks, none = maai_b200.contrastive_loss(x, y, temperature=tau, fused_topk=True)
+        loss_l, logits, labels = maai_b200.contrastive_loss(x, y, temperature=tau, _stash=stash)
+    assert none is None and ranks.dtype == torch.int32 and ranks.shape == (b,)
+    assert abs(float(loss_f) - float(loss_l)) <= 1e-6 * abs(float(loss_l))
+    got = ranks.cpu().numpy()
+    # exact against the same bf16 rows, except where a key is within fp32 rounding of the positive
+    ref_bf, ab, pos = _ranks_from_bf16_rows(stash["z_all"], b, 0, 1)
+    near = (np.abs(ab - pos[:, None]) < 1e-6).sum(1) - 1  # keys tied with the positive up to rounding
+    assert (np.abs(got - ref_bf) <= near).all()
+    # against the fp64 oracle on the original fp32 inputs: bf16 rounding of z may swap near-ties
+    ref = O.positive_rank_oracle([h1.numpy()], [h2.numpy()])[0]
+    assert np.mean(np.abs(got - ref) <= 1) > 0.9 and np.abs(got - ref).max() <= max(3, 0.02 * b)
+    for k in (1, 5):
+        kk = min(k, b)
+        acc_f = float(maai_b200.top_k_accuracy(ranks, None, kk))
+        acc_l = float(maai_b200.top_k_accuracy(logits, labels, kk))
+        assert abs(acc_f - acc_l) <= 2.0 / b
+        assert abs(acc_f - float((ref < kk).mean())) <= max(2.0 / b, 0.01)
+
+
+def test_fused_topk_golden(golden):
+    import maai_b200
+    name = "aligned_b100_d64_t01"
+    h1 = torch.from_numpy(golden[f"{name}.h1"]).cuda(); h2 = torch.from_numpy(golden[f"{name}.h2"]).cuda()
+    with torch.no_grad():
+        loss, ranks, _ = maai_b200.contrastive_loss(h1, h2, temperature=float(golden[f"{name}.tau"]), fused_topk=True)
+    assert abs(float(loss) - float(golden[f"{name}.loss"])) <= LOSS_TOL * abs(float(loss))
+    for k, key in ((1, "top1"), (5, "top5")):
+        assert abs(float(maai_b200.top_k_accuracy(ranks, None, k)) - float(golden[f"{name}.{key}"])) < 1e-6
+    x = h1.clone().requires_grad_(True)
+    with pytest.raises(ValueError):
+        maai_b200.contrastive_loss(x, h2, temperature=0.5, fused_topk=True)

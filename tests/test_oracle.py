@@ -125,3 +125,34 @@ def test_topk_oracle(golden):
         h1, h2 = golden[f"{name}.h1"], golden[f"{name}.h2"]
         assert abs(O.contrastive_topk_oracle(h1, h2, 1) - float(golden[f"{name}.top1"])) < 1e-6
         assert abs(O.contrastive_topk_oracle(h1, h2, 5) - float(golden[f"{name}.top5"])) < 1e-6
+
+
+def test_positive_rank_oracle_matches_topk(golden):
+    """rank-of-positive restatement == the reference's top-k numbers (golden top1/top5 were produced
+    by torch.topk on the imported reference's logits_ab)."""
+    for name in GOLDEN_CASES:
+        h1, h2 = golden[f"{name}.h1"], golden[f"{name}.h2"]
+        r = O.positive_rank_oracle([h1], [h2])[0]
+        for k, key in ((1, "top1"), (5, "top5")):
+            if f"{name}.{key}" in golden:
+                kk = min(k, h1.shape[0])
+                assert abs(float((r < kk).mean()) - float(golden[f"{name}.{key}"])) < 1e-6
+
+
+def test_top_k_accuracy_mirror_both_forms():
+    """Model_Util.top_k_accuracy mirror: reference form (scores + one-hot / index targets,
+    Model_Util.py:104-113) and fused form (pos_rank, None) agree."""
+    import torch
+    import maai_b200
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(50, 120, generator=g)
+    tgt = torch.randint(0, 120, (50,), generator=g)
+    onehot = torch.nn.functional.one_hot(tgt, 120)
+    ranks = (logits > logits[torch.arange(50), tgt][:, None]).sum(1).to(torch.int32)
+    for k in (1, 5, 10):
+        a = maai_b200.top_k_accuracy(logits, tgt, k)
+        b = maai_b200.top_k_accuracy(logits, onehot, k)
+        c = maai_b200.top_k_accuracy(ranks, None, k)
+        assert float(a) == float(b) == float(c)
+    with pytest.raises(TypeError):
+        maai_b200.top_k_accuracy(logits, None, 1)
