@@ -79,6 +79,13 @@
 #endif
 // NQ == 1: 2 = the softmax warps form two teams of 8 that take alternate S tiles (64 columns per
 // thread), 1 = all 16 warps work on every S tile (32 columns per thread).
+// Register redistribution between the control warpgroup and the softmax warpgroups (96 = off).
+#ifndef MAAI_REGS_SM
+#define MAAI_REGS_SM 96
+#endif
+#ifndef MAAI_REGS_WG0
+#define MAAI_REGS_WG0 64
+#endif
 #ifndef MAAI_NQ1_TEAMS
 #define MAAI_NQ1_TEAMS 2
 #endif
@@ -152,7 +159,14 @@ struct TileCfg {
   static constexpr int NB = !BWD ? 4 : (NQ == 2 ? 2 : (D <= 128 ? 3 : 2));
   static constexpr int TMEM_DZ0 = NB * 128;            // BWD accumulators: DZ0 + q*D
   static_assert(!BWD || NB * 128 + NQ * D <= 512, "TMEM budget");
+  // 20 warps: warpgroup 0 = TMA producer, MMA issuer, TMEM allocator, one idle warp; warpgroups
+  // 1-4 = 16 softmax warps.  Launched at 96 registers per thread (65536 / 640); warpgroup 0 then
+  // gives registers back (setmaxnreg.dec) and the softmax warpgroups take them (setmaxnreg.inc).
   static constexpr int NTHREADS = 640;
+  static constexpr int SM_WARP0 = 4;                   // first softmax warp
+  static constexpr int REGS_WG0 = MAAI_REGS_WG0;       // 4 warps x 32 x (96 - REGS_WG0) registers freed
+  static constexpr int REGS_SM = MAAI_REGS_SM;         // 16 warps x 32 x (REGS_SM - 96) taken
+  static_assert(4 * (96 - REGS_WG0) >= 16 * (REGS_SM - 96), "register pool");
   // shared memory carve-up (offsets from a 1024-B aligned base)
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + NQ * TILE_BYTES;
@@ -342,6 +356,10 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  if (C::REGS_SM > 96) {
+    if (warp < C::SM_WARP0) reg_dealloc<C::REGS_WG0>();
+    else reg_alloc<C::REGS_SM>();
+  }
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -512,9 +530,9 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       PROF_MARK(5);
     }
     PROF_FLUSH();
-  } else if (warp >= 4) {
+  } else if (warp >= C::SM_WARP0) {
     // =========================== softmax warps ===========================
-    const int sw = warp - 4;
+    const int sw = warp - C::SM_WARP0;
     const int wgi = sw >> 2;                          // softmax warpgroup 0..3
     constexpr int TEAMS = (NQ == 2) ? 2 : MAAI_NQ1_TEAMS;
     // NQ == 2: team t owns Q tile t.  NQ == 1, two teams: team t takes the S tiles of parity t.
