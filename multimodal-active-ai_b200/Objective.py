@@ -215,8 +215,8 @@ def _validate(hidden1, hidden2, hidden_norm, temperature, world_size, local_rank
                                   "caller uses it")
     if not hidden1.is_cuda or not hidden2.is_cuda:
         raise RuntimeError("maai NT-Xent runs on CUDA (sm_100a) tensors only: there is no CPU fallback")
-    if hidden1.dtype not in _DTYPES or hidden2.dtype != hidden1.dtype:
-        raise TypeError("hidden1/hidden2 must both be float32, bfloat16 or float16")
+    if hidden1.dtype not in _DTYPES or hidden2.dtype not in _DTYPES:
+        raise TypeError("hidden1/hidden2 must be float32, bfloat16 or float16")
     t = float(temperature)
     if not (t >= MIN_TEMPERATURE) or not math.isfinite(t):
         raise ValueError(f"temperature must be >= {MIN_TEMPERATURE} (got {temperature})")
@@ -247,6 +247,11 @@ def contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0, local_
     Returns (loss, logits_ab, labels) like the reference.
     """
     _validate(hidden1, hidden2, hidden_norm, temperature, world_size, local_rank)
+    if hidden1.dtype != hidden2.dtype:
+        # e.g. hidden1 = outputs1.data kept from an autocast forward, hidden2 fp32: compute in the wider
+        # type like the reference's F.normalize / matmul type promotion would
+        wide = torch.promote_types(hidden1.dtype, hidden2.dtype)
+        hidden1, hidden2 = hidden1.to(wide), hidden2.to(wide)
     if fused_topk:
         if torch.is_grad_enabled() and (hidden1.requires_grad or hidden2.requires_grad):
             raise ValueError("fused_topk=True is the validate() path: call it under torch.no_grad() "

@@ -230,3 +230,19 @@ def test_fused_topk_golden(golden):
     x = h1.clone().requires_grad_(True)
     with pytest.raises(ValueError):
         maai_b200.contrastive_loss(x, h2, temperature=0.5, fused_topk=True)
+
+
+@pytest.mark.parametrize("d", [64, 128, 256])
+@pytest.mark.parametrize("tau", [0.1, 0.5])
+@pytest.mark.parametrize("B", [1024, 2048])
+def test_sweep_shapes_parity(B, d, tau):
+    """BASELINE.json configs[4] (sweep d x batch x tau): the shapes tools/sweep.py times, at the sizes
+    the fp64 oracle finishes in seconds."""
+    from oracle import ntxent_oracle as O
+    g = torch.Generator().manual_seed(B + d)
+    h1 = torch.randn(B, d, generator=g).numpy()
+    h2 = torch.randn(B, d, generator=g).numpy()
+    loss, dh1, dh2 = _run(h1, h2, tau)
+    ol, o1, o2 = O.contrastive_loss_oracle(h1, h2, tau)
+    assert abs(loss - ol) <= LOSS_TOL * abs(ol)
+    assert rel_fro(dh1, o1) <= GRAD_TOL and rel_fro(dh2, o2) <= GRAD_TOL
