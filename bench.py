@@ -323,7 +323,11 @@ def main():
         e2e_serial_step()
     e2e_pipelined(args.warmup)
     e2e_serial_s = timed_e2e(lambda k: [e2e_serial_step() for _ in range(k)])
-    e2e_s = timed_e2e(e2e_pipelined)
+    e2e_pipe_s = timed_e2e(e2e_pipelined)
+    # headline = the faster schedule (with several ranks on one host the second copy stream can lose:
+    # N=2 measured 3.4 ms pipelined vs 2.0 ms serial)
+    e2e_s = min(e2e_pipe_s, e2e_serial_s)
+    e2e_mode = "pipelined" if e2e_pipe_s <= e2e_serial_s else "serial"
     e2e_pairs = B * args.steps / e2e_s
     h2d_bytes = 2 * b * d * 4
     d2h = 2 * b * d * 4 + 4
@@ -355,6 +359,13 @@ def main():
         flops_bwd = 16.0 * b * B * d
         achieved = flops_bwd / (bwd_ms * 1e-3) / 1e12 if bwd_ms else None
         step_tflops = 24.0 * B * B * d / (ms * 1e-3) / 1e12 / world
+        traffic = None
+        try:  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tj = json.load(f).get(f"pairs={B},dim={d},n_gpus={world}", {})
+            traffic = next((v for k, v in tj.items() if "BWD" in k), None)
+        except Exception:
+            traffic = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
@@ -366,19 +377,25 @@ def main():
                        "step_tflops_per_gpu_algorithmic": step_tflops,
                        "step_frac_bf16_peak": step_tflops / peaks["bf16"],
                        "ms_median": main_r["ms_median"], "loss": main_r["loss"],
-                       "fwd_call_ms": fwd_ms, "bwd_call_ms": bwd_ms},
+                       "fwd_call_ms": fwd_ms, "bwd_call_ms": bwd_ms,
+                       "span_ms_mean": {k: (statistics.mean(v) if v else None) for k, v in main_r["spans"].items()}},
             "clocks": clocks,
             "e2e": {"value": e2e_pairs, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s / args.steps * 1e3,
+                    "schedule": e2e_mode,
+                    "pipelined_ms_per_step": e2e_pipe_s / args.steps * 1e3,
                     "serial_value": B * args.steps / e2e_serial_s,
                     "serial_ms_per_step": e2e_serial_s / args.steps * 1e3,
                     "what": "every step: pinned host h1,h2 -> device, contrastive_loss + backward, loss + dh1 + dh2 -> "
-                            "pinned host; wall clock over all steps.  value: copies on a second stream, double-buffered "
-                            "(H2D of step i+1 / D2H of step i-1 overlap the kernels of step i); serial_value: one stream, "
-                            "host sync after every step"},
+                            "pinned host; wall clock over all steps.  Two schedules are timed and value is the faster one "
+                            "(schedule): pipelined = copies on a second stream, double-buffered (H2D of step i+1 / D2H of "
+                            "step i-1 overlap the kernels of step i); serial = one stream, host sync after every step"},
             "gpu_launches": int(main_r["launches"]),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
-                         "frac": (achieved / peaks["bf16"]) if achieved else None, "traffic": None,
+                         "frac": (achieved / peaks["bf16"]) if achieved else None, "traffic": traffic,
+                         "traffic_note": "dram read+write bytes per launch, ncu --set full (profiles/r1_ncu_summary_v6.md); "
+                                         "algorithmic HBM bytes of the launch are ~2*2b*d_pad*(2+4) = 101 MB incl. the fp32 "
+                                         "accumulator atomics, most of which stay in L2",
                          "kernel": f"ntxent_tile_kernel<D={maai_b200.padded_dim(d)},BWD,NQ=1>",
                          "how": "16*b*B*d algorithmic flops / mean CUDA-event time of the maai_ntxent_bwd call "
                                 "(memset + tile kernel + dh kernel) over the timed steps",

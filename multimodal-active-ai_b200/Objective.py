@@ -40,7 +40,7 @@ _DTYPES = {torch.float32: _lib.DT_F32, torch.bfloat16: _lib.DT_BF16, torch.float
 class _Profiler:
     """Optional CUDA-event brackets around the C-ABI calls (bench.py's live per-kernel timing)."""
     enabled = False
-    events = {"normalize": [], "fwd": [], "bwd": []}
+    events = {"normalize": [], "gather_z": [], "fwd": [], "gather_r": [], "bwd": []}
 
     @classmethod
     def reset(cls):
@@ -143,14 +143,16 @@ class _NTXentFunction(torch.autograd.Function):
             _lib.check(lib.maai_ntxent_normalize(_ptr(h1), _ptr(h2), b, d, dt, _ptr(z_all[rank]),
                                                  _ptr(inv_norm), _ptr(pos_cos), _stream()),
                        "maai_ntxent_normalize")
-        gather_rows(z_all, rank, group)
+        with _Profiler.span("gather_z"):
+            gather_rows(z_all, rank, group)
         with _Profiler.span("fwd"):
             _lib.check(lib.maai_ntxent_fwd(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(pos_cos),
                                            _ptr(rowsum), _ptr(r_row), _ptr(loss), _stream()),
                        "maai_ntxent_fwd")
         if needs_grad:
             if full:
-                gather_row_factors(r_col, rank, b, world, group)
+                with _Profiler.span("gather_r"):
+                    gather_row_factors(r_col, rank, b, world, group)
             ctx.save_for_backward(h1, h2, z_all, inv_norm, r_row, r_col, pos_cos, rowsum)
             ctx.cfg = (b, d, dp, dt, inv_tau, rank, world, full)
         if stash is not None:
