@@ -176,6 +176,8 @@ def main():
     lib = maai_b200._lib.load()
     peaks = load_peaks()
 
+    from maai_b200.Objective import peer_gather_available
+    peer_mode = world > 1 and peer_gather_available()
     B, d, tau = args.pairs, args.dim, args.tau
     assert B % world == 0
     b = B // world
@@ -372,7 +374,9 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(B, d, tau), "pairs_global": B, "pairs_per_gpu": b,
                        "dim": d, "temperature": tau,
-                       "parallelism": f"dp{world}: anchor rows sharded, bf16 all-gather of z, fp32 all-gather of row factors",
+                       "parallelism": f"dp{world}: anchor rows sharded, bf16 all-gather of z, fp32 all-gather of row factors"
+                                      + ((" -- both fused into the producing kernels as NVLink peer stores + symmetric-memory barrier"
+                                          if peer_mode else " -- NCCL all_gather_into_tensor") if world > 1 else ""),
                        "l2": "flushed between timed steps (256 MiB write outside the event bracket)",
                        "step_tflops_per_gpu_algorithmic": step_tflops,
                        "step_frac_bf16_peak": step_tflops / peaks["bf16"],
@@ -393,9 +397,9 @@ def main():
             "gpu_launches": int(main_r["launches"]),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["bf16"]) if achieved else None, "traffic": traffic,
-                         "traffic_note": "dram read+write bytes per launch, ncu --set full (profiles/r1_ncu_summary_v6.md); "
-                                         "algorithmic HBM bytes of the launch are ~2*2b*d_pad*(2+4) = 101 MB incl. the fp32 "
-                                         "accumulator atomics, most of which stay in L2",
+                         "traffic_note": "dram read+write bytes per launch, ncu --set full (profiles/r1_ncu_summary_v6.md): one pass "
+                                         "over z (16.8 MB) + the fp32 accumulator lines the atomics touch (33.5 MB); the "
+                                         "2Bx2B logits never reach HBM (the reference moves ~100*b*B bytes)",
                          "kernel": f"ntxent_tile_kernel<D={maai_b200.padded_dim(d)},BWD,NQ=1>",
                          "how": "16*b*B*d algorithmic flops / mean CUDA-event time of the maai_ntxent_bwd call "
                                 "(memset + tile kernel + dh kernel) over the timed steps",

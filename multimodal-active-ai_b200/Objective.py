@@ -24,6 +24,7 @@ Differences from the reference, all deliberate:
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -101,6 +102,81 @@ def gather_row_factors(r_col: torch.Tensor, rank: int, b: int, world: int, group
     return r_col
 
 
+class PeerWorkspace:
+    """Symmetric (peer-mapped over NVLink) buffers for the fused gathers of the multi-GPU path.
+
+    Replaces the two collectives of the path -- the bf16 all-gather of the normalised rows
+    (Objective.py:52-53, 102-114) and the fp32 all-gather of the row factors -- by stores issued
+    from the producing kernels themselves (maai_ntxent_normalize_peer, maai_ntxent_fwd_peer) into
+    every rank's buffer, followed by a symmetric-memory barrier (~7 us).  Memory comes from
+    torch.distributed._symmetric_memory (plumbing: allocation, handle exchange, barrier).
+
+    Two buffer sets are used alternately: set i of step t is overwritten by step t+2, which a rank can
+    reach only after every peer has passed the barriers of step t+1, i.e. has finished reading step t.
+    A backward that finds its set overwritten (more than two forwards in flight) raises.
+    """
+    _cache = {}
+    NBUF = 2
+
+    def __init__(self, b, dp, world, rank, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        lib = _lib.load()
+        self.b, self.dp, self.world, self.rank = b, dp, world, rank
+        self.r_len = lib.maai_ntxent_r_len(b, world)
+        zb = world * 2 * b * dp * 2                      # bytes of one key buffer
+        rb = self.r_len * 4                              # bytes of one r array
+        self.zb, self.rb = zb, rb
+        align = lambda x: (x + 255) // 256 * 256
+        self.off_z = [i * align(zb) for i in range(self.NBUF)]
+        self.off_r = [self.NBUF * align(zb) + i * align(rb) for i in range(self.NBUF)]
+        total = self.NBUF * (align(zb) + align(rb))
+        self.raw = symm_mem.empty((total,), dtype=torch.uint8, device=device)
+        self.raw.zero_()                                 # r padding must read as zero
+        self.hdl = symm_mem.rendezvous(self.raw, group if group is not None else dist.group.WORLD)
+        ptrs = list(self.hdl.buffer_ptrs)
+        tab = lambda off: torch.tensor([p + off for p in ptrs], dtype=torch.int64, device=device)
+        self.z_tab = [tab(o) for o in self.off_z]        # device arrays of peer base addresses
+        self.r_tab = [tab(o) for o in self.off_r]
+        self.z = [self.raw[o:o + zb].view(torch.bfloat16).view(world, 2 * b, dp) for o in self.off_z]
+        self.r = [self.raw[o:o + rb].view(torch.float32) for o in self.off_r]
+        self.gen = [0] * self.NBUF
+        self.step = 0
+        torch.cuda.synchronize(device)
+        self.hdl.barrier(channel=0)                      # every rank's zero fill is done before first use
+
+    @classmethod
+    def get(cls, b, dp, world, rank, device, group):
+        key = (b, dp, world, rank, str(device), id(group))
+        ws = cls._cache.get(key)
+        if ws is None:
+            ws = cls._cache[key] = cls(b, dp, world, rank, device, group)
+        return ws
+
+    def next_set(self):
+        i = self.step % self.NBUF
+        self.step += 1
+        self.gen[i] += 1
+        return i, self.gen[i]
+
+
+_peer_state = {"ok": None}
+
+
+def peer_gather_available() -> bool:
+    """True when torch symmetric memory can be used for the fused gathers (probed once)."""
+    if _peer_state["ok"] is None:
+        ok = False
+        if os.environ.get("MAAI_PEER_GATHER", "1") != "0" and dist.is_available() and dist.is_initialized() \
+                and dist.get_backend() == "nccl":
+            try:
+                import torch.distributed._symmetric_memory  # noqa: F401
+                ok = True
+            except Exception:  # noqa: BLE001
+                ok = False
+        _peer_state["ok"] = ok
+    return _peer_state["ok"]
+
+
 def positive_index(b: int, world: int) -> torch.Tensor:
     """Global row index of every global row's positive under the rank-major layout (labels_idx +
     rank*b of Objective.py:55 restated for stacked [view a; view b] blocks)."""
@@ -113,7 +189,7 @@ class _NTXentFunction(torch.autograd.Function):
     """loss = NT-Xent(hidden1, hidden2) for this rank (Objective.py:79), autograd-compatible."""
 
     @staticmethod
-    def forward(ctx, hidden1, hidden2, temperature, rank, world, group, key_grad, stash):
+    def forward(ctx, hidden1, hidden2, temperature, rank, world, group, key_grad, stash, peer=False):
         lib = _lib.load()
         b, d = hidden1.shape
         dev = hidden1.device
@@ -123,14 +199,17 @@ class _NTXentFunction(torch.autograd.Function):
         dt = _DTYPES[h1.dtype]
         inv_tau = 1.0 / float(temperature)
 
+        needs_grad = any(ctx.needs_input_grad[:2])
+        full = bool(key_grad) or world == 1
+        if peer and world > 1:
+            return _NTXentFunction._forward_peer(ctx, h1, h2, dt, inv_tau, rank, world, group, needs_grad, full,
+                                                 stash)
         z_all = torch.empty((world, 2 * b, dp), dtype=torch.bfloat16, device=dev)
         inv_norm = torch.empty(2 * b, dtype=torch.float32, device=dev)
         pos_cos = torch.empty(b, dtype=torch.float32, device=dev)
         rowsum = torch.empty(2 * b, dtype=torch.float32, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
-        needs_grad = any(ctx.needs_input_grad[:2])
         r_len = lib.maai_ntxent_r_len(b, world)
-        full = bool(key_grad) or world == 1
         r_col = torch.zeros(r_len, dtype=torch.float32, device=dev) if needs_grad else None
         if needs_grad and full:
             r_row = r_col[rank * 2 * b:(rank + 1) * 2 * b]  # this rank's slot of the gathered factors
@@ -155,6 +234,54 @@ class _NTXentFunction(torch.autograd.Function):
                     gather_row_factors(r_col, rank, b, world, group)
             ctx.save_for_backward(h1, h2, z_all, inv_norm, r_row, r_col, pos_cos, rowsum)
             ctx.cfg = (b, d, dp, dt, inv_tau, rank, world, full)
+            ctx.peer = None
+        if stash is not None:
+            stash["z_all"] = z_all
+            stash["rowsum"] = rowsum
+            stash["pos_cos"] = pos_cos
+        return loss
+
+    @staticmethod
+    def _forward_peer(ctx, h1, h2, dt, inv_tau, rank, world, group, needs_grad, full, stash):
+        """world > 1 with the gathers fused into the producing kernels (PeerWorkspace)."""
+        lib = _lib.load()
+        b, d = h1.shape
+        dev = h1.device
+        dp = padded_dim(d)
+        ws = PeerWorkspace.get(b, dp, world, rank, dev, group)
+        i, gen = ws.next_set()
+        z_all = ws.z[i]
+        inv_norm = torch.empty(2 * b, dtype=torch.float32, device=dev)
+        pos_cos = torch.empty(b, dtype=torch.float32, device=dev)
+        rowsum = torch.empty(2 * b, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        with _Profiler.span("normalize"):
+            _lib.check(lib.maai_ntxent_normalize_peer(_ptr(h1), _ptr(h2), b, d, dt, _ptr(ws.z_tab[i]), world, rank,
+                                                      _ptr(inv_norm), _ptr(pos_cos), _stream()),
+                       "maai_ntxent_normalize_peer")
+        with _Profiler.span("gather_z"):
+            ws.hdl.barrier(channel=0)  # every rank's rows have landed in every buffer
+        r_row = r_col = None
+        with _Profiler.span("fwd"):
+            if needs_grad and full:
+                _lib.check(lib.maai_ntxent_fwd_peer(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(pos_cos),
+                                                    _ptr(rowsum), _ptr(ws.r_tab[i]), _ptr(loss), _stream()),
+                           "maai_ntxent_fwd_peer")
+            else:
+                if needs_grad:  # keys detached (reference semantics): local row factors only, r_col = 0
+                    r_row = torch.empty(2 * b, dtype=torch.float32, device=dev)
+                    r_col = torch.zeros(ws.r_len, dtype=torch.float32, device=dev)
+                _lib.check(lib.maai_ntxent_fwd(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(pos_cos),
+                                               _ptr(rowsum), _ptr(r_row), _ptr(loss), _stream()), "maai_ntxent_fwd")
+        if needs_grad:
+            if full:
+                with _Profiler.span("gather_r"):
+                    ws.hdl.barrier(channel=1)  # every rank's row factors have landed everywhere
+                r_col = ws.r[i]
+                r_row = r_col[rank * 2 * b:(rank + 1) * 2 * b]
+            ctx.save_for_backward(h1, h2, z_all, inv_norm, r_row, r_col, pos_cos, rowsum)
+            ctx.cfg = (b, d, dp, dt, inv_tau, rank, world, full)
+            ctx.peer = (ws, i, gen)
         if stash is not None:
             stash["z_all"] = z_all
             stash["rowsum"] = rowsum
@@ -166,6 +293,12 @@ class _NTXentFunction(torch.autograd.Function):
         lib = _lib.load()
         h1, h2, z_all, inv_norm, r_row, r_col, pos_cos, rowsum = ctx.saved_tensors
         b, d, dp, dt, inv_tau, rank, world, full = ctx.cfg
+        if ctx.peer is not None:
+            ws, i, gen = ctx.peer
+            if ws.gen[i] != gen:
+                raise RuntimeError("maai NT-Xent: the peer workspace of this forward pass has been overwritten "
+                                   "(more than two forward passes in flight before backward); pass "
+                                   "peer_gather=False to use the NCCL all-gather path")
         need = (1 if ctx.needs_input_grad[0] else 0) | (2 if ctx.needs_input_grad[1] else 0)
         dev = h1.device
         g = grad_loss.to(device=dev, dtype=torch.float32).contiguous()
@@ -178,7 +311,7 @@ class _NTXentFunction(torch.autograd.Function):
                                            _ptr(g), b, world, rank, d, dp, inv_tau, need, _ptr(dh1),
                                            _ptr(dh2), _ptr(dz_acc), _stream()),
                        "maai_ntxent_bwd")
-        return dh1, dh2, None, None, None, None, None, None
+        return dh1, dh2, None, None, None, None, None, None, None
 
 
 def _forward_eval(hidden1, hidden2, temperature, rank, world, group):
@@ -230,7 +363,7 @@ def _validate(hidden1, hidden2, hidden_norm, temperature, world_size, local_rank
 
 def contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0, local_rank=0, world_size=1,
                      device="cpu", *, group=None, key_grad=True, return_logits=None, fused_topk=False,
-                     _stash=None):
+                     peer_gather=None, _stash=None):
     """Drop-in for Objective.contrastive_loss (Objective.py:17-81).
 
     Args (reference): hidden1, hidden2 (bsz, dim); hidden_norm; temperature; local_rank (really the
@@ -238,6 +371,9 @@ def contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0, local_
     Extra keyword-only args: ``group`` process group for the gathers; ``key_grad`` see module doc;
       ``return_logits`` force (True) / suppress (False) the (logits_ab, labels) outputs, default:
       only when autograd is disabled (the validate() path).
+      ``peer_gather`` (world_size > 1): True = the two gathers of the path are fused into the producing
+      kernels as NVLink peer stores + a symmetric-memory barrier (PeerWorkspace); False = NCCL
+      all_gather_into_tensor; None (default) = peer stores when torch symmetric memory is usable.
 
       ``fused_topk=True`` (evaluation only: autograd disabled or no input requires grad): the second
       return value is the int32 vector ``pos_rank`` (bsz,) -- how many view-b keys of all ranks are
@@ -265,8 +401,9 @@ def contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0, local_
     want_logits = (not torch.is_grad_enabled()) if return_logits is None else bool(return_logits)
     if want_logits and stash is None:
         stash = {}
+    peer = (peer_gather_available() if peer_gather is None else bool(peer_gather)) and int(world_size) > 1
     loss = _NTXentFunction.apply(hidden1, hidden2, float(temperature), int(local_rank),
-                                 int(world_size), group, key_grad, stash)
+                                 int(world_size), group, key_grad, stash, peer)
     logits_ab = labels = None
     if want_logits:
         logits_ab, labels = _logits_and_labels(stash["z_all"], hidden1.shape[0], int(local_rank),

@@ -223,7 +223,7 @@ int maai_ntxent_normalize(const void* h1, const void* h2, int b, int d, int in_d
 
 static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
                     const float* pos_cos, float* rowsum_l, float* r_out, float* loss_out,
-                    int* pos_rank, void* stream) {
+                    int* pos_rank, void* stream, const void* const* peer_r = nullptr) {
   if (!z_glob || !pos_cos || !rowsum_l || !loss_out) return fail(MAAI_E_ARG, "null pointer");
   int rc = check_common(b, world, rank);
   if (rc != MAAI_OK) return rc;
@@ -255,7 +255,8 @@ static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, f
                               nullptr, rowsum_l, nullptr, b, b, s);
   }
   if (rc != MAAI_OK) return rc;
-  maai::finalize_loss_kernel<<<maai::kFinalizeCluster, 1024, 0, s>>>(rowsum_l, pos_cos, b, inv_tau, r_out, loss_out);
+  maai::finalize_loss_kernel<<<maai::kFinalizeCluster, 1024, 0, s>>>(
+      rowsum_l, pos_cos, b, inv_tau, r_out, loss_out, reinterpret_cast<const unsigned long long*>(peer_r), world, rank);
   ++g_launches;
   MAAI_CUDA(cudaGetLastError());
   return MAAI_OK;
@@ -266,6 +267,48 @@ int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, f
                     void* stream) {
   return fwd_impl(z_glob, b, world, rank, d_pad, inv_tau, pos_cos, rowsum_l, r_out, loss_out, nullptr,
                   stream);
+}
+
+int maai_ntxent_normalize_peer(const void* h1, const void* h2, int b, int d, int in_dtype,
+                               const void* const* peer_z_bases, int world, int rank, float* inv_norm,
+                               float* pos_cos, void* stream) {
+  if (!h1 || !h2 || !peer_z_bases || !inv_norm || !pos_cos) return fail(MAAI_E_ARG, "null pointer");
+  int rc = check_common(b, world, rank);
+  if (rc != MAAI_OK) return rc;
+  const int dp = maai_padded_dim(d);
+  if (dp < 0) return fail(MAAI_E_SHAPE, "embedding dim must be in [1, 256]");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int wpb = 8;
+  const int grid = (b + wpb - 1) / wpb;
+  const auto* pb = reinterpret_cast<const unsigned long long*>(peer_z_bases);
+#define MAAI_K1P(T, V)                                                                            \
+  maai::normalize_cast_peer_kernel<T, V><<<grid, wpb * 32, 0, s>>>(                               \
+      static_cast<const T*>(h1), static_cast<const T*>(h2), b, d, pb, world, rank, inv_norm, pos_cos)
+#define MAAI_K1P_DP(T)          \
+  switch (dp) {                 \
+    case 64: MAAI_K1P(T, 2); break;  \
+    case 128: MAAI_K1P(T, 4); break; \
+    default: MAAI_K1P(T, 8); break;  \
+  }
+  switch (in_dtype) {
+    case MAAI_DT_F32: MAAI_K1P_DP(float); break;
+    case MAAI_DT_BF16: MAAI_K1P_DP(__nv_bfloat16); break;
+    case MAAI_DT_F16: MAAI_K1P_DP(__half); break;
+    default: return fail(MAAI_E_ARG, "in_dtype must be MAAI_DT_F32, MAAI_DT_BF16 or MAAI_DT_F16");
+  }
+#undef MAAI_K1P_DP
+#undef MAAI_K1P
+  ++g_launches;
+  MAAI_CUDA(cudaGetLastError());
+  return MAAI_OK;
+}
+
+int maai_ntxent_fwd_peer(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
+                         const float* pos_cos, float* rowsum_l, const void* const* peer_r_bases,
+                         float* loss_out, void* stream) {
+  if (!peer_r_bases) return fail(MAAI_E_ARG, "null pointer");
+  return fwd_impl(z_glob, b, world, rank, d_pad, inv_tau, pos_cos, rowsum_l, nullptr, loss_out, nullptr,
+                  stream, peer_r_bases);
 }
 
 int maai_ntxent_fwd_eval(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,

@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cooperative_groups.h>
+#include <type_traits>
 #include "ptx_sm100.cuh"
 
 namespace maai {
@@ -74,17 +75,73 @@ normalize_cast_kernel(const T* __restrict__ h1, const T* __restrict__ h2, int b,
   }
 }
 
+// K1 fused with the embedding all-gather (Objective.py:41-43 + :52-53, 102-114): the normalised bf16
+// rows are stored straight into slot `rank` of EVERY rank's (world, 2b, DP) key buffer through
+// peer-mapped (NVLink) pointers, so no collective kernel runs and the payload crosses the switch
+// while the rows are being produced; a symmetric-memory barrier then orders the stores before any
+// rank's tile kernel reads its buffer.  One warp per pair; a lane owns DP/32 consecutive elements
+// of both rows, so every store is a 4/8/16-byte vector and a warp writes whole 128..512-B rows.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+normalize_cast_peer_kernel(const T* __restrict__ h1, const T* __restrict__ h2, int b, int d,
+                           const unsigned long long* __restrict__ peer_base, int world, int rank,
+                           float* __restrict__ inv_norm, float* __restrict__ pos_cos) {
+  constexpr int DP = VEC * 32;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (k >= b) return;
+  float a[VEC], c[VEC];
+  float sa = 0.f, sc = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int e = lane * VEC + i;
+    a[i] = (e < d) ? to_f32<T>(h1[(size_t)k * d + e]) : 0.f;
+    c[i] = (e < d) ? to_f32<T>(h2[(size_t)k * d + e]) : 0.f;
+    sa += a[i] * a[i];
+    sc += c[i] * c[i];
+  }
+  sa = warp_sum(sa);
+  sc = warp_sum(sc);
+  const float ia = 1.f / fmaxf(sqrtf(sa), kNormEps);
+  const float ic = 1.f / fmaxf(sqrtf(sc), kNormEps);
+  float dot = 0.f;
+  __align__(16) __nv_bfloat16 za[VEC], zc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    za[i] = __float2bfloat16_rn(a[i] * ia);
+    zc[i] = __float2bfloat16_rn(c[i] * ic);
+    dot += __bfloat162float(za[i]) * __bfloat162float(zc[i]);  // same bf16 values the MMA multiplies
+  }
+  dot = warp_sum(dot);
+  using Vec = typename std::conditional<VEC == 2, uint32_t, typename std::conditional<VEC == 4, uint2, uint4>::type>::type;
+  const Vec va = *reinterpret_cast<const Vec*>(za), vc = *reinterpret_cast<const Vec*>(zc);
+  const size_t off_a = (((size_t)rank * 2 * b + k) * DP + lane * VEC) * sizeof(__nv_bfloat16);
+  const size_t off_c = (((size_t)rank * 2 * b + b + k) * DP + lane * VEC) * sizeof(__nv_bfloat16);
+  for (int p = 0; p < world; ++p) {
+    char* base = reinterpret_cast<char*>(peer_base[p]);
+    *reinterpret_cast<Vec*>(base + off_a) = va;
+    *reinterpret_cast<Vec*>(base + off_c) = vc;
+  }
+  if (lane == 0) {
+    inv_norm[k] = ia;
+    inv_norm[b + k] = ic;
+    pos_cos[k] = dot;
+  }
+}
+
 // One thread-block cluster of 8 CTAs (8192 threads), deterministic: fixed thread-strided partial
 // sums in fp64, one value per CTA written into CTA 0's shared memory over DSMEM, summed in rank
 // order.  (A single 1024-thread block took 45 us at 65536 rows, 1.7 % of the step.)
 // With e_pos = exp((cos_pos - 1)/tau) and l' = sum over negatives:
 //   lse_i - s_i,pos = ln(e_pos + l'_i) - ln(e_pos) = log1p(l'_i / e_pos)      (Objective.py:76-77)
 //   loss = (1/b) * sum_{i < 2b} log1p(l'_i / e_pos(i))                          (Objective.py:79)
-// and r_i = 1 / (b * (e_pos + l'_i)) for the backward.  r_out may be null.
+// and r_i = 1 / (b * (e_pos + l'_i)) for the backward.  r_out may be null.  peer_r (optional): device
+// array of `world` peer-mapped base addresses of every rank's gathered r array.
 constexpr int kFinalizeCluster = 8;
 __global__ void __cluster_dims__(kFinalizeCluster, 1, 1) __launch_bounds__(1024)
 finalize_loss_kernel(const float* __restrict__ l, const float* __restrict__ pos_cos, int b,
-                     float inv_tau, float* __restrict__ r_out, float* __restrict__ loss_out) {
+                     float inv_tau, float* __restrict__ r_out, float* __restrict__ loss_out,
+                     const unsigned long long* __restrict__ peer_r = nullptr, int world = 1, int my_rank = 0) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ double part[32];
@@ -97,7 +154,11 @@ finalize_loss_kernel(const float* __restrict__ l, const float* __restrict__ pos_
     const float ln = l[i];
     const float ep = ex2_approx(fmaf(pos_cos[i < b ? i : i - b], c1, -c1));
     acc += double(log1pf(ln / ep));
-    if (r_out) r_out[i] = inv_b / (ep + ln);
+    const float r = inv_b / (ep + ln);
+    if (r_out) r_out[i] = r;
+    if (peer_r) {  // fused all-gather of the row factors: slot `rank` of every rank's r array (NVLink stores)
+      for (int p = 0; p < world; ++p) reinterpret_cast<float*>(peer_r[p])[(size_t)my_rank * 2 * b + i] = r;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
