@@ -74,17 +74,20 @@ int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, f
  * through peer-mapped pointers (NVLink / NVSwitch stores issued by the kernel itself, no collective
  * launch).  The caller orders the stores before any rank reads with a symmetric-memory barrier.
  *   peer_z_bases  DEVICE array of `world` device pointers: entry p = base address, as mapped into this
- *                 process, of rank p's key buffer (entry `rank` is the local buffer) */
+ *                 process, of rank p's key buffer (entry `rank` is the local buffer)
+ *   mc_z_base     NVLink multicast (multimem) address of the same buffers, or NULL: when given, each
+ *                 row is stored ONCE and the NVSwitch replicates it into every rank's buffer */
 int maai_ntxent_normalize_peer(const void* h1, const void* h2, int b, int d, int in_dtype,
-                               const void* const* peer_z_bases, int world, int rank, float* inv_norm,
-                               float* pos_cos, void* stream);
+                               const void* const* peer_z_bases, void* mc_z_base, int world, int rank,
+                               float* inv_norm, float* pos_cos, void* stream);
 
 /* K2 fused with the all-gather of the row factors: like maai_ntxent_fwd, but r_i is stored into slot
  * `rank` of every rank's gathered r array (maai_ntxent_r_len floats each, zero padded by the owner).
- *   peer_r_bases  DEVICE array of `world` peer-mapped base addresses of the r arrays */
+ *   peer_r_bases  DEVICE array of `world` peer-mapped base addresses of the r arrays
+ *   mc_r_base     multicast address of the r arrays, or NULL */
 int maai_ntxent_fwd_peer(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
                          const float* pos_cos, float* rowsum_l, const void* const* peer_r_bases,
-                         float* loss_out, void* stream);
+                         void* mc_r_base, float* loss_out, void* stream);
 
 /* K2 for validate() (Contrastive_Learning.py:860-868): the same forward plus, for every view-a anchor
  * k of this rank, pos_rank[k] = number of view-b keys of ALL ranks whose similarity to the anchor is

@@ -139,6 +139,16 @@ class PeerWorkspace:
         self.r_tab = [tab(o) for o in self.off_r]
         self.z = [self.raw[o:o + zb].view(torch.bfloat16).view(world, 2 * b, dp) for o in self.off_z]
         self.r = [self.raw[o:o + rb].view(torch.float32) for o in self.off_r]
+        # NVSwitch multicast mapping of the same allocation (one store reaches every rank), if the
+        # fabric offers it; MAAI_PEER_MULTICAST=0 forces per-peer unicast stores
+        mc = 0
+        try:
+            if os.environ.get("MAAI_PEER_MULTICAST", "1") != "0":
+                mc = int(self.hdl.multicast_ptr)
+        except Exception:  # noqa: BLE001
+            mc = 0
+        self.mc_z = [mc + o if mc else None for o in self.off_z]
+        self.mc_r = [mc + o if mc else None for o in self.off_r]
         self.gen = [0] * self.NBUF
         self.step = 0
         torch.cuda.synchronize(device)
@@ -256,8 +266,8 @@ class _NTXentFunction(torch.autograd.Function):
         rowsum = torch.empty(2 * b, dtype=torch.float32, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
         with _Profiler.span("normalize"):
-            _lib.check(lib.maai_ntxent_normalize_peer(_ptr(h1), _ptr(h2), b, d, dt, _ptr(ws.z_tab[i]), world, rank,
-                                                      _ptr(inv_norm), _ptr(pos_cos), _stream()),
+            _lib.check(lib.maai_ntxent_normalize_peer(_ptr(h1), _ptr(h2), b, d, dt, _ptr(ws.z_tab[i]), ws.mc_z[i],
+                                                      world, rank, _ptr(inv_norm), _ptr(pos_cos), _stream()),
                        "maai_ntxent_normalize_peer")
         with _Profiler.span("gather_z"):
             ws.hdl.barrier(channel=0)  # every rank's rows have landed in every buffer
@@ -265,7 +275,8 @@ class _NTXentFunction(torch.autograd.Function):
         with _Profiler.span("fwd"):
             if needs_grad and full:
                 _lib.check(lib.maai_ntxent_fwd_peer(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(pos_cos),
-                                                    _ptr(rowsum), _ptr(ws.r_tab[i]), _ptr(loss), _stream()),
+                                                    _ptr(rowsum), _ptr(ws.r_tab[i]), ws.mc_r[i], _ptr(loss),
+                                                    _stream()),
                            "maai_ntxent_fwd_peer")
             else:
                 if needs_grad:  # keys detached (reference semantics): local row factors only, r_col = 0

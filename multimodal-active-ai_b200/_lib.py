@@ -25,10 +25,10 @@ SIGNATURES = {
                                        _c_void_p, _c_void_p, _c_void_p]),
     "maai_ntxent_fwd": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p,
                                  _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
-    "maai_ntxent_normalize_peer": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_int,
-                                            _c_int, _c_void_p, _c_void_p, _c_void_p]),
+    "maai_ntxent_normalize_peer": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
+                                            _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
     "maai_ntxent_fwd_peer": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p,
-                                      _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+                                      _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "maai_ntxent_fwd_eval": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p,
                                       _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "maai_ntxent_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,

@@ -223,7 +223,7 @@ int maai_ntxent_normalize(const void* h1, const void* h2, int b, int d, int in_d
 
 static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
                     const float* pos_cos, float* rowsum_l, float* r_out, float* loss_out,
-                    int* pos_rank, void* stream, const void* const* peer_r = nullptr) {
+                    int* pos_rank, void* stream, const void* const* peer_r = nullptr, void* mc_r = nullptr) {
   if (!z_glob || !pos_cos || !rowsum_l || !loss_out) return fail(MAAI_E_ARG, "null pointer");
   int rc = check_common(b, world, rank);
   if (rc != MAAI_OK) return rc;
@@ -256,7 +256,8 @@ static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, f
   }
   if (rc != MAAI_OK) return rc;
   maai::finalize_loss_kernel<<<maai::kFinalizeCluster, 1024, 0, s>>>(
-      rowsum_l, pos_cos, b, inv_tau, r_out, loss_out, reinterpret_cast<const unsigned long long*>(peer_r), world, rank);
+      rowsum_l, pos_cos, b, inv_tau, r_out, loss_out, reinterpret_cast<const unsigned long long*>(peer_r), world, rank,
+      static_cast<float*>(mc_r));
   ++g_launches;
   MAAI_CUDA(cudaGetLastError());
   return MAAI_OK;
@@ -270,8 +271,8 @@ int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, f
 }
 
 int maai_ntxent_normalize_peer(const void* h1, const void* h2, int b, int d, int in_dtype,
-                               const void* const* peer_z_bases, int world, int rank, float* inv_norm,
-                               float* pos_cos, void* stream) {
+                               const void* const* peer_z_bases, void* mc_z_base, int world, int rank,
+                               float* inv_norm, float* pos_cos, void* stream) {
   if (!h1 || !h2 || !peer_z_bases || !inv_norm || !pos_cos) return fail(MAAI_E_ARG, "null pointer");
   int rc = check_common(b, world, rank);
   if (rc != MAAI_OK) return rc;
@@ -283,7 +284,8 @@ int maai_ntxent_normalize_peer(const void* h1, const void* h2, int b, int d, int
   const auto* pb = reinterpret_cast<const unsigned long long*>(peer_z_bases);
 #define MAAI_K1P(T, V)                                                                            \
   maai::normalize_cast_peer_kernel<T, V><<<grid, wpb * 32, 0, s>>>(                               \
-      static_cast<const T*>(h1), static_cast<const T*>(h2), b, d, pb, world, rank, inv_norm, pos_cos)
+      static_cast<const T*>(h1), static_cast<const T*>(h2), b, d, pb,                              \
+      reinterpret_cast<unsigned long long>(mc_z_base), world, rank, inv_norm, pos_cos)
 #define MAAI_K1P_DP(T)          \
   switch (dp) {                 \
     case 64: MAAI_K1P(T, 2); break;  \
@@ -305,10 +307,10 @@ int maai_ntxent_normalize_peer(const void* h1, const void* h2, int b, int d, int
 
 int maai_ntxent_fwd_peer(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
                          const float* pos_cos, float* rowsum_l, const void* const* peer_r_bases,
-                         float* loss_out, void* stream) {
+                         void* mc_r_base, float* loss_out, void* stream) {
   if (!peer_r_bases) return fail(MAAI_E_ARG, "null pointer");
   return fwd_impl(z_glob, b, world, rank, d_pad, inv_tau, pos_cos, rowsum_l, nullptr, loss_out, nullptr,
-                  stream, peer_r_bases);
+                  stream, peer_r_bases, mc_r_base);
 }
 
 int maai_ntxent_fwd_eval(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,

@@ -75,6 +75,22 @@ normalize_cast_kernel(const T* __restrict__ h1, const T* __restrict__ h2, int b,
   }
 }
 
+// store through an NVLink multicast (multimem) address: every device of the multicast object gets it
+__device__ __forceinline__ void multimem_st(void* a, uint32_t v) {
+  asm volatile("multimem.st.weak.global.bf16x2 [%0], %1;" ::"l"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_st(void* a, uint2 v) {
+  asm volatile("multimem.st.weak.global.v2.bf16x2 [%0], {%1, %2};" ::"l"(a), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void multimem_st(void* a, uint4 v) {
+  asm volatile("multimem.st.weak.global.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(a), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void multimem_st_f32(float* a, float v) {
+  asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(a), "f"(v) : "memory");
+}
+
 // K1 fused with the embedding all-gather (Objective.py:41-43 + :52-53, 102-114): the normalised bf16
 // rows are stored straight into slot `rank` of EVERY rank's (world, 2b, DP) key buffer through
 // peer-mapped (NVLink) pointers, so no collective kernel runs and the payload crosses the switch
@@ -84,8 +100,8 @@ normalize_cast_kernel(const T* __restrict__ h1, const T* __restrict__ h2, int b,
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 normalize_cast_peer_kernel(const T* __restrict__ h1, const T* __restrict__ h2, int b, int d,
-                           const unsigned long long* __restrict__ peer_base, int world, int rank,
-                           float* __restrict__ inv_norm, float* __restrict__ pos_cos) {
+                           const unsigned long long* __restrict__ peer_base, unsigned long long mc_base,
+                           int world, int rank, float* __restrict__ inv_norm, float* __restrict__ pos_cos) {
   constexpr int DP = VEC * 32;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -117,10 +133,17 @@ normalize_cast_peer_kernel(const T* __restrict__ h1, const T* __restrict__ h2, i
   const Vec va = *reinterpret_cast<const Vec*>(za), vc = *reinterpret_cast<const Vec*>(zc);
   const size_t off_a = (((size_t)rank * 2 * b + k) * DP + lane * VEC) * sizeof(__nv_bfloat16);
   const size_t off_c = (((size_t)rank * 2 * b + b + k) * DP + lane * VEC) * sizeof(__nv_bfloat16);
-  for (int p = 0; p < world; ++p) {
-    char* base = reinterpret_cast<char*>(peer_base[p]);
-    *reinterpret_cast<Vec*>(base + off_a) = va;
-    *reinterpret_cast<Vec*>(base + off_c) = vc;
+  if (mc_base) {
+    // NVSwitch multicast mapping of the same buffers: ONE store, replicated into every rank's copy by
+    // the switch (multimem.st), instead of `world` unicast stores
+    multimem_st(reinterpret_cast<char*>(mc_base) + off_a, va);
+    multimem_st(reinterpret_cast<char*>(mc_base) + off_c, vc);
+  } else {
+    for (int p = 0; p < world; ++p) {
+      char* base = reinterpret_cast<char*>(peer_base[p]);
+      *reinterpret_cast<Vec*>(base + off_a) = va;
+      *reinterpret_cast<Vec*>(base + off_c) = vc;
+    }
   }
   if (lane == 0) {
     inv_norm[k] = ia;
@@ -141,7 +164,8 @@ constexpr int kFinalizeCluster = 8;
 __global__ void __cluster_dims__(kFinalizeCluster, 1, 1) __launch_bounds__(1024)
 finalize_loss_kernel(const float* __restrict__ l, const float* __restrict__ pos_cos, int b,
                      float inv_tau, float* __restrict__ r_out, float* __restrict__ loss_out,
-                     const unsigned long long* __restrict__ peer_r = nullptr, int world = 1, int my_rank = 0) {
+                     const unsigned long long* __restrict__ peer_r = nullptr, int world = 1, int my_rank = 0,
+                     float* mc_r = nullptr) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ double part[32];
@@ -156,7 +180,10 @@ finalize_loss_kernel(const float* __restrict__ l, const float* __restrict__ pos_
     acc += double(log1pf(ln / ep));
     const float r = inv_b / (ep + ln);
     if (r_out) r_out[i] = r;
-    if (peer_r) {  // fused all-gather of the row factors: slot `rank` of every rank's r array (NVLink stores)
+    // fused all-gather of the row factors: slot `rank` of every rank's r array (NVLink stores)
+    if (mc_r) {
+      multimem_st_f32(mc_r + (size_t)my_rank * 2 * b + i, r);
+    } else if (peer_r) {
       for (int p = 0; p < world; ++p) reinterpret_cast<float*>(peer_r[p])[(size_t)my_rank * 2 * b + i] = r;
     }
   }
