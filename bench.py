@@ -201,9 +201,9 @@ def main():
         loss.backward()
         return loss
 
-    def timed_run(bb, steps, warmup, profile):
+    def timed_run(bb, steps, warmup, profile, grad1=True):
         h1, h2 = make_inputs(bb)
-        x = h1.requires_grad_(True)
+        x = h1.requires_grad_(grad1)
         y = h2.requires_grad_(True)
         for _ in range(warmup):
             step(x, y)
@@ -342,6 +342,14 @@ def main():
                      "pairs_per_s": 4096 / (s["ms_per_step"] * 1e-3),
                      "frac_bf16_peak": 24.0 * 4096 ** 2 * d / (s["ms_per_step"] * 1e-3) / (peaks["bf16"] * 1e12)}
 
+    # ---------------- secondary: the reference's training call, hidden1 detached ----------------
+    # (Contrastive_Learning.py:685-690 passes hidden1=outputs1.data: only dh2 is needed, half of the backward)
+    detached = None
+    if not args.no_secondary:
+        s2 = timed_run(b, max(args.steps // 2, 20), args.warmup, profile=False, grad1=False)
+        detached = {"workload": workload_name(B, d, tau).replace("both inputs require grad", "hidden1 detached (training call)"),
+                    "ms_per_step": s2["ms_per_step"], "pairs_per_s": B / (s2["ms_per_step"] * 1e-3)}
+
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -409,6 +417,8 @@ def main():
         }
         if secondary:
             line["config"]["configs1_4096_pairs"] = secondary
+        if detached:
+            line["config"]["hidden1_detached"] = detached
         emit(line)
     if world > 1:
         dist.destroy_process_group()

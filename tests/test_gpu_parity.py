@@ -246,3 +246,49 @@ def test_sweep_shapes_parity(B, d, tau):
     ol, o1, o2 = O.contrastive_loss_oracle(h1, h2, tau)
     assert abs(loss - ol) <= LOSS_TOL * abs(ol)
     assert rel_fro(dh1, o1) <= GRAD_TOL and rel_fro(dh2, o2) <= GRAD_TOL
+
+
+def test_c_abi_is_cuda_graph_capturable():
+    """include/maai_ntxent.h: every call only enqueues work (no allocation, no sync): the whole
+    forward + backward is captured into one CUDA graph through the C ABI and replayed on new inputs."""
+    from maai_b200 import _lib
+    from oracle import ntxent_oracle as O
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    b, d, tau = 320, 128, 0.5
+    dp = lib.maai_padded_dim(d)
+    h1 = torch.zeros(b, d, device=dev); h2 = torch.zeros(b, d, device=dev)
+    z = torch.empty(1, 2 * b, dp, dtype=torch.bfloat16, device=dev)
+    inv = torch.empty(2 * b, device=dev); cos = torch.empty(b, device=dev); l = torch.empty(2 * b, device=dev)
+    r = torch.zeros(lib.maai_ntxent_r_len(b, 1), device=dev); loss = torch.zeros((), device=dev)
+    g1 = torch.zeros(b, d, device=dev); g2 = torch.zeros(b, d, device=dev)
+    acc = torch.empty(2 * b, dp, device=dev); one = torch.ones((), device=dev)
+
+    def enqueue(stream):
+        _lib.check(lib.maai_ntxent_normalize(h1.data_ptr(), h2.data_ptr(), b, d, 0, z.data_ptr(), inv.data_ptr(),
+                                             cos.data_ptr(), stream), "k1")
+        _lib.check(lib.maai_ntxent_fwd(z.data_ptr(), b, 1, 0, dp, 1.0 / tau, cos.data_ptr(), l.data_ptr(),
+                                       r.data_ptr(), loss.data_ptr(), stream), "k2")
+        _lib.check(lib.maai_ntxent_bwd(z.data_ptr(), r.data_ptr(), r.data_ptr(), 1, l.data_ptr(), cos.data_ptr(),
+                                       h1.data_ptr(), h2.data_ptr(), 0, inv.data_ptr(), one.data_ptr(), b, 1, 0, d, dp,
+                                       1.0 / tau, 3, g1.data_ptr(), g2.data_ptr(), acc.data_ptr(), stream), "k3")
+
+    gen = torch.Generator().manual_seed(5)
+    a0 = torch.randn(b, d, generator=gen); c0 = torch.randn(b, d, generator=gen)
+    h1.copy_(a0); h2.copy_(c0)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        enqueue(s.cuda_stream)  # warm-up outside capture (function attributes, tensor-map entry point)
+    s.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s):
+        enqueue(torch.cuda.current_stream().cuda_stream)
+    for seed in (6, 7):
+        gen = torch.Generator().manual_seed(seed)
+        a = torch.randn(b, d, generator=gen); c = a + 0.5 * torch.randn(b, d, generator=gen)
+        h1.copy_(a); h2.copy_(c)
+        graph.replay()
+        torch.cuda.synchronize()
+        ol, o1, o2 = O.contrastive_loss_oracle(a.numpy(), c.numpy(), tau)
+        assert abs(float(loss) - ol) <= LOSS_TOL * abs(ol)
+        assert rel_fro(g1.cpu().numpy(), o1) <= GRAD_TOL and rel_fro(g2.cpu().numpy(), o2) <= GRAD_TOL
