@@ -69,6 +69,46 @@ int make_rows_tmap(CUtensorMap* m, const void* base, int rows, int d_pad) {
   return MAAI_OK;
 }
 
+// Optional programmatic stream serialization (PDL) for every kernel of the library: with MAAI_PDL=1
+// (and a build with MAAI_PDL_TRIG != 0) the next kernel's launch latency and prologue overlap the tail
+// of the previous one; each kernel calls griddepcontrol.wait before it touches global memory.  Off by
+// default: see the note at MAAI_PDL_TRIG in ptx_sm100.cuh.
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("MAAI_PDL");
+    return v && v[0] == '1';
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  ++g_launches;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+int zero_words(void* p, size_t n_words, cudaStream_t s) {
+  if (n_words == 0) return MAAI_OK;
+  size_t blocks = (n_words / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 592) blocks = 592;
+  --g_launches;  // bookkeeping kernels are not counted in gpu_launches (they replaced memsets)
+  cudaError_t e = launch_k(maai::zero_kernel, dim3((unsigned)blocks), dim3(256), 0, s, static_cast<uint32_t*>(p), n_words);
+  if (e != cudaSuccess) return cuda_fail("zero_kernel", e);
+  return MAAI_OK;
+}
+
 int sm_count() {
   static int n = [] {
     int dev = 0, v = 0;
@@ -124,9 +164,8 @@ int launch_tile(const void* q_base, int m_loc, const void* k_base, int m_glob, i
   int sms = sm_count();
   if (sms <= 0) return fail(MAAI_E_CUDA, "no CUDA device");
   const int grid = (int)(items < sms ? items : sms);
-  maai::ntxent_tile_kernel<D, BWD, NQ, RANK><<<grid, C::NTHREADS, C::SMEM_BYTES, s>>>(tq, tk, p);
-  ++g_launches;
-  MAAI_CUDA(cudaGetLastError());
+  MAAI_CUDA(launch_k(maai::ntxent_tile_kernel<D, BWD, NQ, RANK>, dim3(grid), dim3(C::NTHREADS), C::SMEM_BYTES, s,
+                     tq, tk, p));
   return MAAI_OK;
 }
 
@@ -199,25 +238,25 @@ int maai_ntxent_normalize(const void* h1, const void* h2, int b, int d, int in_d
   const int wpb = 8;
   const int grid = (b + wpb - 1) / wpb;
   auto* z = static_cast<__nv_bfloat16*>(z_out);
+  cudaError_t e;
   switch (in_dtype) {
     case MAAI_DT_F32:
-      maai::normalize_cast_kernel<float><<<grid, wpb * 32, 0, s>>>(
-          static_cast<const float*>(h1), static_cast<const float*>(h2), b, d, dp, z, inv_norm, pos_cos);
+      e = launch_k(maai::normalize_cast_kernel<float>, dim3(grid), dim3(wpb * 32), 0, s,
+                   static_cast<const float*>(h1), static_cast<const float*>(h2), b, d, dp, z, inv_norm, pos_cos);
       break;
     case MAAI_DT_BF16:
-      maai::normalize_cast_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, s>>>(
-          static_cast<const __nv_bfloat16*>(h1), static_cast<const __nv_bfloat16*>(h2), b, d, dp, z,
-          inv_norm, pos_cos);
+      e = launch_k(maai::normalize_cast_kernel<__nv_bfloat16>, dim3(grid), dim3(wpb * 32), 0, s,
+                   static_cast<const __nv_bfloat16*>(h1), static_cast<const __nv_bfloat16*>(h2), b, d, dp, z,
+                   inv_norm, pos_cos);
       break;
     case MAAI_DT_F16:
-      maai::normalize_cast_kernel<__half><<<grid, wpb * 32, 0, s>>>(
-          static_cast<const __half*>(h1), static_cast<const __half*>(h2), b, d, dp, z, inv_norm, pos_cos);
+      e = launch_k(maai::normalize_cast_kernel<__half>, dim3(grid), dim3(wpb * 32), 0, s,
+                   static_cast<const __half*>(h1), static_cast<const __half*>(h2), b, d, dp, z, inv_norm, pos_cos);
       break;
     default:
       return fail(MAAI_E_ARG, "in_dtype must be MAAI_DT_F32, MAAI_DT_BF16 or MAAI_DT_F16");
   }
-  ++g_launches;
-  MAAI_CUDA(cudaGetLastError());
+  MAAI_CUDA(e);
   return MAAI_OK;
 }
 
@@ -231,12 +270,12 @@ static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, f
   if (!aligned16(z_glob)) return fail(MAAI_E_ARG, "z_glob must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int m_loc = 2 * b, m_glob = 2 * b * world;
-  MAAI_CUDA(cudaMemsetAsync(rowsum_l, 0, sizeof(float) * m_loc, s));
+  if ((rc = zero_words(rowsum_l, (size_t)m_loc, s)) != MAAI_OK) return rc;
   const char* q_base = static_cast<const char*>(z_glob) + (size_t)rank * m_loc * d_pad * 2;
   if (pos_rank) {
     // evaluation forward: same kernel + the rank of every view-a anchor's positive among the
     // view-b keys (one instantiation per padded width, the forward's default tile layout)
-    MAAI_CUDA(cudaMemsetAsync(pos_rank, 0, sizeof(int) * b, s));
+    if ((rc = zero_words(pos_rank, (size_t)b, s)) != MAAI_OK) return rc;
     RankArgs ra;
     ra.pos_cos = pos_cos;
     ra.rank_out = pos_rank;
@@ -255,11 +294,9 @@ static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, f
                               nullptr, rowsum_l, nullptr, b, b, s);
   }
   if (rc != MAAI_OK) return rc;
-  maai::finalize_loss_kernel<<<maai::kFinalizeCluster, 1024, 0, s>>>(
-      rowsum_l, pos_cos, b, inv_tau, r_out, loss_out, reinterpret_cast<const unsigned long long*>(peer_r), world, rank,
-      static_cast<float*>(mc_r));
-  ++g_launches;
-  MAAI_CUDA(cudaGetLastError());
+  MAAI_CUDA(launch_k(maai::finalize_loss_kernel, dim3(maai::kFinalizeCluster), dim3(1024), 0, s,
+                     static_cast<const float*>(rowsum_l), pos_cos, b, inv_tau, r_out, loss_out,
+                     reinterpret_cast<const unsigned long long*>(peer_r), world, rank, static_cast<float*>(mc_r)));
   return MAAI_OK;
 }
 
@@ -282,10 +319,11 @@ int maai_ntxent_normalize_peer(const void* h1, const void* h2, int b, int d, int
   const int wpb = 8;
   const int grid = (b + wpb - 1) / wpb;
   const auto* pb = reinterpret_cast<const unsigned long long*>(peer_z_bases);
+  cudaError_t e = cudaSuccess;
 #define MAAI_K1P(T, V)                                                                            \
-  maai::normalize_cast_peer_kernel<T, V><<<grid, wpb * 32, 0, s>>>(                               \
-      static_cast<const T*>(h1), static_cast<const T*>(h2), b, d, pb,                              \
-      reinterpret_cast<unsigned long long>(mc_z_base), world, rank, inv_norm, pos_cos)
+  e = launch_k(maai::normalize_cast_peer_kernel<T, V>, dim3(grid), dim3(wpb * 32), 0, s,          \
+               static_cast<const T*>(h1), static_cast<const T*>(h2), b, d, pb,                     \
+               reinterpret_cast<unsigned long long>(mc_z_base), world, rank, inv_norm, pos_cos)
 #define MAAI_K1P_DP(T)          \
   switch (dp) {                 \
     case 64: MAAI_K1P(T, 2); break;  \
@@ -300,8 +338,7 @@ int maai_ntxent_normalize_peer(const void* h1, const void* h2, int b, int d, int
   }
 #undef MAAI_K1P_DP
 #undef MAAI_K1P
-  ++g_launches;
-  MAAI_CUDA(cudaGetLastError());
+  MAAI_CUDA(e);
   return MAAI_OK;
 }
 
@@ -341,7 +378,7 @@ int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, 
   const int row_begin = (need_mask == 2) ? b : 0;
   const int rows = (need_mask == 3) ? m_loc : b;
   float* acc = dz_acc + (size_t)row_begin * d_pad;
-  MAAI_CUDA(cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)rows * d_pad, s));
+  if ((rc = zero_words(acc, (size_t)rows * d_pad, s)) != MAAI_OK) return rc;
   const char* q_base =
       static_cast<const char*>(z_glob) + ((size_t)rank * m_loc + row_begin) * d_pad * 2;
   rc = dispatch_tile<true>(d_pad, q_base, rows, z_glob, m_glob, rank * m_loc + row_begin, inv_tau,
@@ -349,29 +386,29 @@ int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, 
   if (rc != MAAI_OK) return rc;
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
+  const float* dza = dz_acc;
+  cudaError_t e;
   switch (in_dtype) {
     case MAAI_DT_F32:
-      maai::dh_kernel<float><<<grid, wpb * 32, 0, s>>>(
-          dz_acc, static_cast<const float*>(h1), static_cast<const float*>(h2), inv_norm, grad_loss, rowsum_l,
-          pos_cos, b, d, d_pad, inv_tau, key_grad, need_mask, static_cast<float*>(dh1), static_cast<float*>(dh2));
+      e = launch_k(maai::dh_kernel<float>, dim3(grid), dim3(wpb * 32), 0, s, dza, static_cast<const float*>(h1),
+                   static_cast<const float*>(h2), inv_norm, grad_loss, rowsum_l, pos_cos, b, d, d_pad, inv_tau,
+                   key_grad, need_mask, static_cast<float*>(dh1), static_cast<float*>(dh2));
       break;
     case MAAI_DT_BF16:
-      maai::dh_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, s>>>(
-          dz_acc, static_cast<const __nv_bfloat16*>(h1), static_cast<const __nv_bfloat16*>(h2),
-          inv_norm, grad_loss, rowsum_l, pos_cos, b, d, d_pad, inv_tau, key_grad, need_mask, static_cast<__nv_bfloat16*>(dh1),
-          static_cast<__nv_bfloat16*>(dh2));
+      e = launch_k(maai::dh_kernel<__nv_bfloat16>, dim3(grid), dim3(wpb * 32), 0, s, dza,
+                   static_cast<const __nv_bfloat16*>(h1), static_cast<const __nv_bfloat16*>(h2), inv_norm, grad_loss,
+                   rowsum_l, pos_cos, b, d, d_pad, inv_tau, key_grad, need_mask, static_cast<__nv_bfloat16*>(dh1),
+                   static_cast<__nv_bfloat16*>(dh2));
       break;
     case MAAI_DT_F16:
-      maai::dh_kernel<__half><<<grid, wpb * 32, 0, s>>>(
-          dz_acc, static_cast<const __half*>(h1), static_cast<const __half*>(h2), inv_norm, grad_loss,
-          rowsum_l, pos_cos, b, d, d_pad, inv_tau, key_grad, need_mask,
-          static_cast<__half*>(dh1), static_cast<__half*>(dh2));
+      e = launch_k(maai::dh_kernel<__half>, dim3(grid), dim3(wpb * 32), 0, s, dza, static_cast<const __half*>(h1),
+                   static_cast<const __half*>(h2), inv_norm, grad_loss, rowsum_l, pos_cos, b, d, d_pad, inv_tau,
+                   key_grad, need_mask, static_cast<__half*>(dh1), static_cast<__half*>(dh2));
       break;
     default:
       return fail(MAAI_E_ARG, "in_dtype must be MAAI_DT_F32, MAAI_DT_BF16 or MAAI_DT_F16");
   }
-  ++g_launches;
-  MAAI_CUDA(cudaGetLastError());
+  MAAI_CUDA(e);
   return MAAI_OK;
 }
 

@@ -40,6 +40,8 @@ normalize_cast_kernel(const T* __restrict__ h1, const T* __restrict__ h2, int b,
                       float* __restrict__ pos_cos) {
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents<1>();
+  pdl_wait();
   if (k >= b) return;
   float a[kMaxPerLane], c[kMaxPerLane];
   float sa = 0.f, sc = 0.f;
@@ -105,6 +107,8 @@ normalize_cast_peer_kernel(const T* __restrict__ h1, const T* __restrict__ h2, i
   constexpr int DP = VEC * 32;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents<1>();
+  pdl_wait();
   if (k >= b) return;
   float a[VEC], c[VEC];
   float sa = 0.f, sc = 0.f;
@@ -171,6 +175,8 @@ finalize_loss_kernel(const float* __restrict__ l, const float* __restrict__ pos_
   __shared__ double part[32];
   __shared__ double cta_part[kFinalizeCluster];  // CTA 0's copy collects one value per CTA
   const unsigned rank = cluster.block_rank();
+  pdl_launch_dependents<8>();
+  pdl_wait();
   double acc = 0.0;
   const float inv_b = 1.f / float(b);
   const float c1 = inv_tau * 1.4426950408889634f;
@@ -206,6 +212,20 @@ finalize_loss_kernel(const float* __restrict__ l, const float* __restrict__ pos_
   }
 }
 
+// Zero fill of an accumulator (replaces cudaMemsetAsync so that the launch chain stays programmatic).
+__global__ void __launch_bounds__(256) zero_kernel(uint32_t* __restrict__ p, size_t n_words) {
+  pdl_launch_dependents<2>();
+  pdl_wait();
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+    uint4* p4 = reinterpret_cast<uint4*>(p);
+    for (size_t i = tid; i < n_words / 4; i += nth) p4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (size_t i = (n_words / 4) * 4 + tid; i < n_words; i += nth) p[i] = 0u;
+  } else {
+    for (size_t i = tid; i < n_words; i += nth) p[i] = 0u;
+  }
+}
+
 // One warp per anchor row i of the views that need a gradient.
 //   dz_i = (g / tau) * (A_i + cpos_i z_pos(i)),  A = dz_acc (fp32, stride dp, positive column excluded)
 //   cpos_i = [e_pos/(e_pos + l'_i) - 1]/b  (+ the same with l'_pos when the key side is kept)
@@ -221,6 +241,8 @@ dh_kernel(const float* __restrict__ dz_acc, const T* __restrict__ h1, const T* _
           float inv_tau, int key_grad, int need_mask, T* __restrict__ dh1, T* __restrict__ dh2) {
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents<16>();
+  pdl_wait();
   // rows are enumerated over the views that need a gradient
   const int both = (need_mask == 3);
   const int nrows = both ? 2 * b : b;

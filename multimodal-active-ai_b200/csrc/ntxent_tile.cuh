@@ -43,7 +43,7 @@
 // Of every 8 column pairs a softmax thread handles, this many take the polynomial exp2 on the FMA
 // pipe instead of MUFU.EX2 (build-time knobs so the split can be A/B-measured).
 #ifndef MAAI_POLY_FWD
-#define MAAI_POLY_FWD 4
+#define MAAI_POLY_FWD 3
 #endif
 #ifndef MAAI_POLY_BWD
 #define MAAI_POLY_BWD 0
@@ -323,6 +323,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents<4>();
 
   // ---- this CTA's contiguous range of (row block, key tile) items ----
   const long long total = (long long)p.nrb * p.nkt;

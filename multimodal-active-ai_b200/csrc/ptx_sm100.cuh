@@ -13,6 +13,29 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (no-ops when the kernel was launched without the attribute)
+// ----------------------------------------------------------------------------------------------
+// Let the next kernel of the stream start launching (its prologue overlaps this kernel's work) ...
+// Which kernels release their dependents early: 1 normalize, 2 zero, 4 tile, 8 finalize, 16 dh.
+// Default 0 = none, and the launch attribute itself is off unless MAAI_PDL=1 (maai_ntxent.cu).
+// Measured with all five triggering: configs[1] (4096 pairs) step 0.142 -> 0.120 ms, but a CUDA-graph
+// replay of two back-to-back steps (tests/test_gpu_parity.py::test_c_abi_is_cuda_graph_capturable)
+// then returns a wrong loss / wrong gradients -- also for subsets in which no persistent tile kernel
+// triggers (bisected with tools/ab_variants.py, profiles/r1_tuning_log.md).  Every kernel waits
+// (griddepcontrol.wait) before its first global access, so the chain should be transitive; until the
+// ordering hole is understood the early triggers stay compiled out.
+#ifndef MAAI_PDL_TRIG
+#define MAAI_PDL_TRIG 0
+#endif
+template <int WHO>
+__device__ __forceinline__ void pdl_launch_dependents() {
+  if (MAAI_PDL_TRIG & WHO) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// ... and, in that next kernel, wait until the previous kernel has completed and its writes are
+// visible.  Must precede every global-memory access that depends on (or could clobber) earlier work.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

@@ -249,33 +249,41 @@ def test_sweep_shapes_parity(B, d, tau):
 
 
 def test_c_abi_is_cuda_graph_capturable():
-    """include/maai_ntxent.h: every call only enqueues work (no allocation, no sync): the whole
-    forward + backward is captured into one CUDA graph through the C ABI and replayed on new inputs."""
+    """include/maai_ntxent.h: every call only enqueues work (no allocation, no sync): TWO consecutive
+    forward + backward passes (different inputs, separate buffers) are captured into one CUDA graph
+    through the C ABI and replayed on new inputs.  Back-to-back replay is also the tightest schedule
+    the kernels ever see, so this doubles as the ordering test of the programmatic launch chain."""
     from maai_b200 import _lib
     from oracle import ntxent_oracle as O
     lib = _lib.load()
     dev = torch.device("cuda:0")
     b, d, tau = 320, 128, 0.5
     dp = lib.maai_padded_dim(d)
-    h1 = torch.zeros(b, d, device=dev); h2 = torch.zeros(b, d, device=dev)
-    z = torch.empty(1, 2 * b, dp, dtype=torch.bfloat16, device=dev)
-    inv = torch.empty(2 * b, device=dev); cos = torch.empty(b, device=dev); l = torch.empty(2 * b, device=dev)
-    r = torch.zeros(lib.maai_ntxent_r_len(b, 1), device=dev); loss = torch.zeros((), device=dev)
-    g1 = torch.zeros(b, d, device=dev); g2 = torch.zeros(b, d, device=dev)
-    acc = torch.empty(2 * b, dp, device=dev); one = torch.ones((), device=dev)
+
+    class Bufs:
+        def __init__(self):
+            self.h1 = torch.zeros(b, d, device=dev); self.h2 = torch.zeros(b, d, device=dev)
+            self.z = torch.empty(1, 2 * b, dp, dtype=torch.bfloat16, device=dev)
+            self.inv = torch.empty(2 * b, device=dev); self.cos = torch.empty(b, device=dev)
+            self.l = torch.empty(2 * b, device=dev)
+            self.r = torch.zeros(lib.maai_ntxent_r_len(b, 1), device=dev); self.loss = torch.zeros((), device=dev)
+            self.g1 = torch.zeros(b, d, device=dev); self.g2 = torch.zeros(b, d, device=dev)
+            self.acc = torch.empty(2 * b, dp, device=dev)
+
+    one = torch.ones((), device=dev)
+    steps = [Bufs(), Bufs()]
 
     def enqueue(stream):
-        _lib.check(lib.maai_ntxent_normalize(h1.data_ptr(), h2.data_ptr(), b, d, 0, z.data_ptr(), inv.data_ptr(),
-                                             cos.data_ptr(), stream), "k1")
-        _lib.check(lib.maai_ntxent_fwd(z.data_ptr(), b, 1, 0, dp, 1.0 / tau, cos.data_ptr(), l.data_ptr(),
-                                       r.data_ptr(), loss.data_ptr(), stream), "k2")
-        _lib.check(lib.maai_ntxent_bwd(z.data_ptr(), r.data_ptr(), r.data_ptr(), 1, l.data_ptr(), cos.data_ptr(),
-                                       h1.data_ptr(), h2.data_ptr(), 0, inv.data_ptr(), one.data_ptr(), b, 1, 0, d, dp,
-                                       1.0 / tau, 3, g1.data_ptr(), g2.data_ptr(), acc.data_ptr(), stream), "k3")
+        for t in steps:
+            _lib.check(lib.maai_ntxent_normalize(t.h1.data_ptr(), t.h2.data_ptr(), b, d, 0, t.z.data_ptr(),
+                                                 t.inv.data_ptr(), t.cos.data_ptr(), stream), "k1")
+            _lib.check(lib.maai_ntxent_fwd(t.z.data_ptr(), b, 1, 0, dp, 1.0 / tau, t.cos.data_ptr(), t.l.data_ptr(),
+                                           t.r.data_ptr(), t.loss.data_ptr(), stream), "k2")
+            _lib.check(lib.maai_ntxent_bwd(t.z.data_ptr(), t.r.data_ptr(), t.r.data_ptr(), 1, t.l.data_ptr(),
+                                           t.cos.data_ptr(), t.h1.data_ptr(), t.h2.data_ptr(), 0, t.inv.data_ptr(),
+                                           one.data_ptr(), b, 1, 0, d, dp, 1.0 / tau, 3, t.g1.data_ptr(),
+                                           t.g2.data_ptr(), t.acc.data_ptr(), stream), "k3")
 
-    gen = torch.Generator().manual_seed(5)
-    a0 = torch.randn(b, d, generator=gen); c0 = torch.randn(b, d, generator=gen)
-    h1.copy_(a0); h2.copy_(c0)
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         enqueue(s.cuda_stream)  # warm-up outside capture (function attributes, tensor-map entry point)
@@ -283,12 +291,17 @@ def test_c_abi_is_cuda_graph_capturable():
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph, stream=s):
         enqueue(torch.cuda.current_stream().cuda_stream)
-    for seed in (6, 7):
-        gen = torch.Generator().manual_seed(seed)
-        a = torch.randn(b, d, generator=gen); c = a + 0.5 * torch.randn(b, d, generator=gen)
-        h1.copy_(a); h2.copy_(c)
+    for seed in (6, 7, 8):
+        ins = []
+        for k, t in enumerate(steps):
+            gen = torch.Generator().manual_seed(10 * seed + k)
+            a = torch.randn(b, d, generator=gen); c = a + 0.5 * torch.randn(b, d, generator=gen)
+            t.h1.copy_(a); t.h2.copy_(c)
+            ins.append((a, c))
         graph.replay()
+        graph.replay()  # twice back to back: the second replay's first kernels chase the first's last
         torch.cuda.synchronize()
-        ol, o1, o2 = O.contrastive_loss_oracle(a.numpy(), c.numpy(), tau)
-        assert abs(float(loss) - ol) <= LOSS_TOL * abs(ol)
-        assert rel_fro(g1.cpu().numpy(), o1) <= GRAD_TOL and rel_fro(g2.cpu().numpy(), o2) <= GRAD_TOL
+        for (a, c), t in zip(ins, steps):
+            ol, o1, o2 = O.contrastive_loss_oracle(a.numpy(), c.numpy(), tau)
+            assert abs(float(t.loss) - ol) <= LOSS_TOL * abs(ol)
+            assert rel_fro(t.g1.cpu().numpy(), o1) <= GRAD_TOL and rel_fro(t.g2.cpu().numpy(), o2) <= GRAD_TOL
