@@ -86,6 +86,15 @@
 #ifndef MAAI_REGS_WG0
 #define MAAI_REGS_WG0 64
 #endif
+// Symmetric forward, tiles above the diagonal: of the 4 column blocks (8 columns) of each 32-column
+// chunk, this many take the polynomial exp2 (chunk 0 / chunk 1).  Measured best: none (these tiles
+// already carry the column-sum work on the FMA / ALU pipes and are MUFU-bound at half the tile count).
+#ifndef MAAI_POLY_SYM0
+#define MAAI_POLY_SYM0 0
+#endif
+#ifndef MAAI_POLY_SYM1
+#define MAAI_POLY_SYM1 0
+#endif
 #ifndef MAAI_NQ1_TEAMS
 #define MAAI_NQ1_TEAMS 2
 #endif
@@ -294,7 +303,37 @@ __device__ __forceinline__ void softmax_chunk(uint32_t (&v)[CW], uint32_t (&pk)[
   CX_MARK(2);
 }
 
-template <int D, bool BWD, int NQ, bool RANK = false>
+// Walks the CTA's item range segment by segment (a segment = a maximal run of key tiles inside one
+// row block).  SYM (symmetric forward, anchors == keys): row block rb only visits key tiles
+// kt >= 2*rb, because E_ij = E_ji lets every tile above the diagonal contribute its row sums to the
+// anchors AND its column sums to the keys; the tiles below the diagonal are never computed.
+template <bool SYM>
+struct SegWalk {
+  int nkt;
+  int rb = 0;
+  long long cum = 0;  // items before row block rb
+  __device__ __forceinline__ explicit SegWalk(int nkt_) : nkt(nkt_) {}
+  __device__ __forceinline__ int cnt(int r) const { return SYM ? nkt - 2 * r : nkt; }
+  // segment that starts at item `it`: row block, first key tile, number of key tiles
+  __device__ __forceinline__ void locate(long long it, long long it_end, int& rb_out, int& j0, int& n) {
+    if (SYM) {
+      while (it >= cum + cnt(rb)) {
+        cum += cnt(rb);
+        ++rb;
+      }
+      const int off = int(it - cum);
+      rb_out = rb;
+      j0 = 2 * rb + off;
+      n = int(min((long long)(cnt(rb) - off), it_end - it));
+    } else {
+      rb_out = int(it / nkt);
+      j0 = int(it % nkt);
+      n = int(min((long long)(nkt - j0), it_end - it));
+    }
+  }
+};
+
+template <int D, bool BWD, int NQ, bool RANK = false, bool SYM = false>
 __global__ void __launch_bounds__(640, 1)
 ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
                    const __grid_constant__ CUtensorMap tmap_k, const TileParams p) {
@@ -326,7 +365,10 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
   pdl_launch_dependents<4>();
 
   // ---- this CTA's contiguous range of (row block, key tile) items ----
-  const long long total = (long long)p.nrb * p.nkt;
+  static_assert(!SYM || (!BWD && !RANK && NQ == 2 && MAAI_FWD_CW == 32),
+                "symmetric mode: plain forward, two Q tiles per row block, 32-column chunks");
+  const long long total = SYM ? (long long)p.nrb * p.nkt - (long long)p.nrb * (p.nrb - 1)
+                              : (long long)p.nrb * p.nkt;
   const long long it_begin = total * blockIdx.x / gridDim.x;
   const long long it_end = total * (blockIdx.x + 1) / gridDim.x;
 
@@ -367,9 +409,10 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
     if (lane == 0) {
       PROF_INIT();
       uint32_t t = 0, useg = 0;
+      SegWalk<SYM> walk(p.nkt);
       for (long long it = it_begin; it < it_end;) {
-        const int rb = int(it / p.nkt), j0 = int(it % p.nkt);
-        const int n = int(min((long long)(p.nkt - j0), it_end - it));
+        int rb, j0, n;
+        walk.locate(it, it_end, rb, j0, n);
         mbar_wait(bar_q_empty, (useg & 1) ^ 1);
         PROF_MARK(0);
         mbar_arrive_expect_tx(bar_q_full, NQ * C::TILE_BYTES);
@@ -474,10 +517,12 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       PROF_MARK(3);
     };
 
+    SegWalk<SYM> walk(p.nkt);
+    uint32_t symu[2] = {0, 0};  // SYM: S tiles issued so far per team (a team skips tiles below the diagonal)
 #pragma unroll 1
     for (long long it = it_begin; it < it_end;) {
-      const int j0 = int(it % p.nkt);
-      const int n = int(min((long long)(p.nkt - j0), it_end - it));
+      int rb, j0, n;
+      walk.locate(it, it_end, rb, j0, n);
       mbar_wait(bar_q_full, useg & 1);
       tc_fence_after();
       PROF_MARK(0);
@@ -495,7 +540,25 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
         issue_s(sg0 + s, q, st);
       };
-      if (!BWD) {
+      if (!BWD && SYM) {
+#pragma unroll 1
+        for (int jj = 0; jj < n; ++jj) {
+          const uint32_t tk = t + jj;
+          const int st = tk % NST;
+          mbar_wait(bar_k_full(st), (tk / NST) & 1);
+          tc_fence_after();
+          PROF_MARK(0);
+          // Q tile 1 of the row block sits one key tile further down the diagonal: its tile with the
+          // first key tile of the block (kt == 2 rb) lies below the diagonal and is not computed
+          const int nq_here = (j0 + jj < 2 * rb + 1) ? 1 : 2;
+          for (int q = 0; q < nq_here; ++q) {
+            issue_s(symu[q] * 2 + q, q, st);
+            ++symu[q];
+          }
+          commit(bar_k_empty(st));
+        }
+        commit(bar_q_empty);
+      } else if (!BWD) {
 #pragma unroll 1
         for (int s = 0; s < ns; ++s) {
           issue_s_local(s);
@@ -573,10 +636,14 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
     for (int i = 0; i < 8; ++i) cx.prof_a[i] = 0;
 #endif
 
+    SegWalk<SYM> walk(p.nkt);
+    // SYM: partial row sums of the tiles above the diagonal, in the 16x256b fragment layout: slot k of
+    // a thread is tile row 32 w4 + 8 k + lane / 4 (k = 0..3), summed over the thread's columns
+    float2 racc_m[4], racc_p[4];
 #pragma unroll 1
     for (long long it = it_begin; it < it_end;) {
-      const int rb = int(it / p.nkt), j0 = int(it % p.nkt);
-      const int n = int(min((long long)(p.nkt - j0), it_end - it));
+      int rb, j0, n;
+      walk.locate(it, it_end, rb, j0, n);
       const int q = (NQ == 2) ? team : 0;
       const int row = rb * C::RB_ROWS + q * 128 + row_in_tile;  // anchor row (local)
       const bool valid = row < p.m_loc;
@@ -600,10 +667,19 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
       float2 acc_m[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       float2 acc_p[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      bool any_upper = false;
+      if (SYM) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) racc_m[k] = racc_p[k] = make_float2(0.f, 0.f);
+      }
 
 #pragma unroll 1
       for (int jj = 0; jj < n; ++jj) {
         const int kt = j0 + jj;
+        // SYM: key tile kt against row tile 2 rb + q: below the diagonal -> not computed at all,
+        // on it -> ordinary tile (row sums), above it -> row sums AND column sums
+        if (SYM && kt < 2 * rb + q) continue;
+        const bool upper = SYM && kt > 2 * rb + q;
         const int buf = (NQ == 2) ? team * MODB + sb : sb;
         const bool special = unsigned(kt - kt_d) <= 1u || unsigned(kt - kt_p1) <= 1u ||
                              unsigned(kt - kt_p2) <= 1u || kt == kt_ragged;
@@ -626,9 +702,110 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
           if (BWD) mbar_wait(bar_k_full(kst), kph);  // r_j of this stage has landed
           mbar_wait(bar_s_full(buf), sph);
           tc_fence_after();
-          tmem_ld_cw(s_addr, v0);
+          if (!upper) tmem_ld_cw(s_addr, v0);
         }
         CX_MARK(0);
+        if (SYM && upper) {
+          // ---------------- tile above the diagonal: E_ij serves row i and column j ----------------
+          any_upper = true;
+          const uint32_t t_base = tmem_base + buf * 128 + col_off;
+          const int r_lo = w4 * 32 + (lane >> 2);          // tile row of slot 0; slot k adds 8 k
+          const int c_lo = 2 * (lane & 3);                 // first of the thread's two columns per 8-column block
+          constexpr int PG[2] = {MAAI_POLY_SYM0, MAAI_POLY_SYM1};  // polynomial column blocks (of 4) per chunk
+          const float2 c1p = make_float2(c1, c1), c1n = make_float2(-c1, -c1);
+          float2 colp[4];  // column partial sums of the current chunk over this thread's 4 rows
+          uint32_t v[16];
+          auto load_half = [&](int c, int h) {
+            tmem_ld_16x256b_x4(t_base + (uint32_t(w4 * 32 + h * 16) << 16) + c * 32, v);
+          };
+          // one 16-lane half of the warp's 32 rows at a time (16 registers in flight; loading both
+          // halves first was measured 15 % slower: more live registers, spills)
+          auto half = [&](int c, int h, float2 (&cp)[4]) {
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) asm volatile("" : "+r"(v[i]));
+            float2 e[8];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+#pragma unroll
+              for (int hi = 0; hi < 2; ++hi) {
+                const float2 sv = make_float2(__uint_as_float(v[4 * g + 2 * hi]), __uint_as_float(v[4 * g + 2 * hi + 1]));
+                if (g < PG[c]) {
+                  e[2 * g + hi] = exp2_dot_poly2<DEG>(sv, c1p);
+                } else {
+                  const float2 x = __ffma2_rn(sv, c1p, c1n);
+                  e[2 * g + hi].x = ex2_approx(x.x);
+                  e[2 * g + hi].y = ex2_approx(x.y);
+                }
+              }
+            }
+            // the registers are free again: start the next load before the sums (and, for the last
+            // half, hand the S buffer back: every column of the tile is in registers)
+            if (!(c == 1 && h == 1)) {
+              load_half(h == 1 ? c + 1 : c, h ^ 1);
+            } else {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_sm_done(buf));
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+#pragma unroll
+              for (int hi = 0; hi < 2; ++hi) {
+                float2 ev = e[2 * g + hi];
+                const int k = 2 * h + hi;  // row slot
+                if (special) {  // the positive of a view-a row, keys past the end
+                  const int lr = rb * C::RB_ROWS + q * 128 + r_lo + 8 * k;
+                  const int gr = p.row_global_base + lr;
+                  const int gp = lr < p.pos_split ? gr + p.pos_delta : gr - p.pos_delta;
+                  const int kc = kt * C::KT + col_off + c * 32 + 8 * g + c_lo;
+                  if (kc == gp || kc == gr || kc >= p.m_glob) ev.x = 0.f;
+                  if (kc + 1 == gp || kc + 1 == gr || kc + 1 >= p.m_glob) ev.y = 0.f;
+                }
+                if (g < PG[c]) racc_p[k] = __fadd2_rn(racc_p[k], ev);
+                else racc_m[k] = __fadd2_rn(racc_m[k], ev);
+                cp[g] = (h == 0 && hi == 0) ? ev : __fadd2_rn(cp[g], ev);
+              }
+            }
+          };
+          // column sums over the warp's 32 rows: the 8 lanes that share lane % 4 hold the same 8
+          // columns; three exchange stages leave one column per lane
+          auto col_flush = [&](int c, const float2 (&cp)[4]) {
+            const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+            const float a[8] = {cp[0].x, cp[0].y, cp[1].x, cp[1].y, cp[2].x, cp[2].y, cp[3].x, cp[3].y};
+            float s4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float send = b4 ? a[i] : a[i + 4], keep = b4 ? a[i + 4] : a[i];
+              s4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+            float s2[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float send = b3 ? s4[i] : s4[i + 2], keep = b3 ? s4[i + 2] : s4[i];
+              s2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            const float send = b2 ? s2[0] : s2[1], keep = b2 ? s2[1] : s2[0];
+            float cs = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            // this lane now owns value index 4 b4 + 2 b3 + b2 = 2 g + parity of the 8
+            const int gsel = (b4 ? 2 : 0) + (b3 ? 1 : 0);
+            if (gsel < PG[c]) cs *= kscale;
+            const int key = kt * C::KT + col_off + c * 32 + 8 * gsel + c_lo + (b2 ? 1 : 0);
+            if (key < p.m_loc) atomicAdd(p.l_out + key, cs);
+          };
+          load_half(0, 0);
+          half(0, 0, colp);
+          half(0, 1, colp);
+          col_flush(0, colp);  // the first load of chunk 1 is in flight
+          half(1, 0, colp);
+          half(1, 1, colp);
+          col_flush(1, colp);
+          if (++sb == MODB) { sb = 0; sph ^= 1; }
+          if (++kst == NST) { kst = 0; kph ^= 1; }
+          tpar ^= 1;
+          CX_MARK(3);
+          continue;
+        }
         // ring positions of the tile after this one; probe its barriers now (non-blocking), use
         // the answer when the last chunk of this tile has been loaded
         int sb_n = sb + 1, kst_n = kst + 1;
@@ -726,6 +903,16 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
           const float2 sm = __fadd2_rn(acc_m[0], acc_m[1]), sp = __fadd2_rn(acc_p[0], acc_p[1]);
           atomicAdd(p.l_out + row, (sm.x + sm.y) + kscale * (sp.x + sp.y));
           if (RANK && row < p.pos_split && cx.cnt) atomicAdd(p.rank_out + row, cx.cnt);
+        }
+        if (SYM && any_upper) {  // fragment-layout partial row sums: 4 lanes per row
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float v = (racc_m[k].x + racc_m[k].y) + kscale * (racc_p[k].x + racc_p[k].y);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            const int lr = rb * C::RB_ROWS + q * 128 + w4 * 32 + 8 * k + (lane >> 2);
+            if ((lane & 3) == 0 && lr < p.m_loc) atomicAdd(p.l_out + lr, v);
+          }
         }
       } else {
         mbar_wait(bar_dz_full, useg & 1);

@@ -253,6 +253,21 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x 256 bit (8 columns), x4 = 32 columns: thread t of the warp gets, in register 4g + k,
+// lane (t / 4) + 8 (k >> 1) of the 16 addressed lanes and column 8 g + 2 (t % 4) + (k & 1)
+// (verified on hardware by tools/tmem_layout.cu).  A thread therefore holds two rows x eight columns:
+// the register layout of an mma accumulator fragment, which makes column sums cheap (three shuffle
+// stages over the 8 lanes that share t % 4) -- used by the symmetric forward.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "

@@ -305,3 +305,34 @@ def test_c_abi_is_cuda_graph_capturable():
             ol, o1, o2 = O.contrastive_loss_oracle(a.numpy(), c.numpy(), tau)
             assert abs(float(t.loss) - ol) <= LOSS_TOL * abs(ol)
             assert rel_fro(t.g1.cpu().numpy(), o1) <= GRAD_TOL and rel_fro(t.g2.cpu().numpy(), o2) <= GRAD_TOL
+
+
+@pytest.mark.parametrize("b,d,tau,aligned", [(64, 128, 0.5, False), (100, 64, 0.1, True), (129, 128, 0.5, False),
+                                              (1000, 128, 0.5, True), (37, 20, 0.5, False), (2048, 128, 0.1, True)])
+def test_symmetric_forward_forced(b, d, tau, aligned):
+    """The symmetric forward (tiles on / above the diagonal only, column sums through the 16x256b
+    fragment layout) is switched on by size; here it is forced (MAAI_FWD_SYM=1, read per call) on small,
+    ragged and straddling shapes and compared with the fp64 oracle and with the full-tile forward."""
+    import os
+    import maai_b200
+    from oracle import ntxent_oracle as O
+    g = torch.Generator().manual_seed(11 * b + d)
+    h1 = torch.randn(b, d, generator=g)
+    h2 = h1 + 0.7 * torch.randn(b, d, generator=g) if aligned else torch.randn(b, d, generator=g)
+    res = {}
+    old = os.environ.get("MAAI_FWD_SYM")
+    try:
+        for mode in ("1", "0"):
+            os.environ["MAAI_FWD_SYM"] = mode
+            res[mode] = _run(h1.numpy(), h2.numpy(), tau)
+    finally:
+        if old is None:
+            os.environ.pop("MAAI_FWD_SYM", None)
+        else:
+            os.environ["MAAI_FWD_SYM"] = old
+    ol, o1, o2 = O.contrastive_loss_oracle(h1.numpy(), h2.numpy(), tau)
+    for mode in ("1", "0"):
+        loss, dh1, dh2 = res[mode]
+        assert abs(loss - ol) <= LOSS_TOL * abs(ol), mode
+        assert rel_fro(dh1, o1) <= GRAD_TOL and rel_fro(dh2, o2) <= GRAD_TOL, mode
+    assert abs(res["1"][0] - res["0"][0]) <= 1e-5 * abs(ol)
