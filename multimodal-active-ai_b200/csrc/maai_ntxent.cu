@@ -291,12 +291,11 @@ static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, f
     }
 #undef MAAI_LAUNCH_RANK
   } else if (world == 1 && (d_pad == 64 || d_pad == 128) && env_int("MAAI_DEBUG_FWD_NQ", 2) == 2 &&
-             (env_int("MAAI_FWD_SYM", -1) == 1 ||
-              (env_int("MAAI_FWD_SYM", -1) == -1 && d_pad == 128 && m_loc >= env_int("MAAI_FWD_SYM_MIN_ROWS", 16384)))) {
+             env_int("MAAI_FWD_SYM", 1) != 0) {
     // Single rank: anchors == keys and E_ij = E_ji, so only the tiles on and above the diagonal are
     // computed; a tile above it adds its row sums to the anchors and its column sums to the keys
-    // (half the MMAs and exp2s; measured -12 % forward time and -8 % step time at 32768 pairs, d=128
-    // under sustained load, no gain at d=64 or below ~8192 pairs: MAAI_FWD_SYM=0/1 forces off / on).
+    // (half the MMAs and exp2s; measured forward 0.955 -> 0.724 ms at 32768 pairs, d=128, 0.884 -> 0.726
+    // at d=64, step -12.6 % under sustained load; MAAI_FWD_SYM=0 selects the full-tile forward).
     if (d_pad == 64)
       rc = launch_tile<64, false, 2, false, true>(q_base, m_loc, z_glob, m_glob, 0, inv_tau, nullptr, nullptr,
                                                   rowsum_l, nullptr, b, b, s);

@@ -87,13 +87,13 @@
 #define MAAI_REGS_WG0 64
 #endif
 // Symmetric forward, tiles above the diagonal: of the 4 column blocks (8 columns) of each 32-column
-// chunk, this many take the polynomial exp2 (chunk 0 / chunk 1).  Measured best: none (these tiles
-// already carry the column-sum work on the FMA / ALU pipes and are MUFU-bound at half the tile count).
+// chunk, this many take the polynomial exp2 (chunk 0 / chunk 1).  Measured best: 1 + 1 (these tiles
+// already carry the column-sum work on the FMA / ALU pipes; 0+0 is 2.5 % slower, 2+1 3 % slower).
 #ifndef MAAI_POLY_SYM0
-#define MAAI_POLY_SYM0 0
+#define MAAI_POLY_SYM0 1
 #endif
 #ifndef MAAI_POLY_SYM1
-#define MAAI_POLY_SYM1 0
+#define MAAI_POLY_SYM1 1
 #endif
 #ifndef MAAI_NQ1_TEAMS
 #define MAAI_NQ1_TEAMS 2
@@ -748,20 +748,26 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
               __syncwarp();
               if (lane == 0) mbar_arrive(bar_sm_done(buf));
             }
+            if (special) {  // one branch per half: the positive of a view-a row, keys past the end
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+#pragma unroll
+                for (int hi = 0; hi < 2; ++hi) {
+                  const int lr = rb * C::RB_ROWS + q * 128 + r_lo + 8 * (2 * h + hi);
+                  const int gr = p.row_global_base + lr;
+                  const int gp = lr < p.pos_split ? gr + p.pos_delta : gr - p.pos_delta;
+                  const int kc = kt * C::KT + col_off + c * 32 + 8 * g + c_lo;
+                  if (kc == gp || kc == gr || kc >= p.m_glob) e[2 * g + hi].x = 0.f;
+                  if (kc + 1 == gp || kc + 1 == gr || kc + 1 >= p.m_glob) e[2 * g + hi].y = 0.f;
+                }
+              }
+            }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
 #pragma unroll
               for (int hi = 0; hi < 2; ++hi) {
-                float2 ev = e[2 * g + hi];
+                const float2 ev = e[2 * g + hi];
                 const int k = 2 * h + hi;  // row slot
-                if (special) {  // the positive of a view-a row, keys past the end
-                  const int lr = rb * C::RB_ROWS + q * 128 + r_lo + 8 * k;
-                  const int gr = p.row_global_base + lr;
-                  const int gp = lr < p.pos_split ? gr + p.pos_delta : gr - p.pos_delta;
-                  const int kc = kt * C::KT + col_off + c * 32 + 8 * g + c_lo;
-                  if (kc == gp || kc == gr || kc >= p.m_glob) ev.x = 0.f;
-                  if (kc + 1 == gp || kc + 1 == gr || kc + 1 >= p.m_glob) ev.y = 0.f;
-                }
                 if (g < PG[c]) racc_p[k] = __fadd2_rn(racc_p[k], ev);
                 else racc_m[k] = __fadd2_rn(racc_m[k], ev);
                 cp[g] = (h == 0 && hi == 0) ? ev : __fadd2_rn(cp[g], ev);
