@@ -187,6 +187,27 @@ def peer_gather_available() -> bool:
     return _peer_state["ok"]
 
 
+def _peer_usable(b, dp, world, rank, device, group) -> bool:
+    """Automatic mode: build the workspace for this shape once; every rank then votes (all_reduce MIN)
+    so that either all of them take the peer path or all take the NCCL path.  A box on which symmetric
+    memory cannot be set up (no P2P mapping, container restrictions) silently keeps the NCCL gathers."""
+    key = ("usable", b, dp, world, rank, str(device), id(group))
+    ok = _peer_state.get(key)
+    if ok is None:
+        good = 1
+        try:
+            PeerWorkspace.get(b, dp, world, rank, device, group)
+        except Exception as e:  # noqa: BLE001
+            good = 0
+            if rank == 0:
+                import warnings
+                warnings.warn(f"maai NT-Xent: symmetric memory unavailable ({e!r}); using NCCL all_gather")
+        flag = torch.tensor([good], device=device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        ok = _peer_state[key] = bool(int(flag.item()))
+    return ok
+
+
 def positive_index(b: int, world: int) -> torch.Tensor:
     """Global row index of every global row's positive under the rank-major layout (labels_idx +
     rank*b of Objective.py:55 restated for stacked [view a; view b] blocks)."""
@@ -412,7 +433,13 @@ def contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0, local_
     want_logits = (not torch.is_grad_enabled()) if return_logits is None else bool(return_logits)
     if want_logits and stash is None:
         stash = {}
-    peer = (peer_gather_available() if peer_gather is None else bool(peer_gather)) and int(world_size) > 1
+    peer = False
+    if int(world_size) > 1:
+        if peer_gather is None:
+            peer = peer_gather_available() and _peer_usable(hidden1.shape[0], padded_dim(hidden1.shape[1]),
+                                                            int(world_size), int(local_rank), hidden1.device, group)
+        else:
+            peer = bool(peer_gather)
     loss = _NTXentFunction.apply(hidden1, hidden2, float(temperature), int(local_rank),
                                  int(world_size), group, key_grad, stash, peer)
     logits_ab = labels = None
