@@ -176,8 +176,10 @@ def main():
     lib = maai_b200._lib.load()
     peaks = load_peaks()
 
-    from maai_b200.Objective import peer_gather_available
-    peer_mode = world > 1 and peer_gather_available()
+    from maai_b200.Objective import _peer_state
+
+    def peer_mode_used():  # decided (and voted on by the ranks) at the first call with a given shape
+        return world > 1 and any(v for k, v in _peer_state.items() if isinstance(k, tuple) and k[0] == "usable")
     B, d, tau = args.pairs, args.dim, args.tau
     assert B % world == 0
     b = B // world
@@ -384,7 +386,7 @@ def main():
                        "dim": d, "temperature": tau,
                        "parallelism": f"dp{world}: anchor rows sharded, bf16 all-gather of z, fp32 all-gather of row factors"
                                       + ((" -- both fused into the producing kernels as NVLink peer stores + symmetric-memory barrier"
-                                          if peer_mode else " -- NCCL all_gather_into_tensor") if world > 1 else ""),
+                                          if peer_mode_used() else " -- NCCL all_gather_into_tensor") if world > 1 else ""),
                        "l2": "flushed between timed steps (256 MiB write outside the event bracket)",
                        "step_tflops_per_gpu_algorithmic": step_tflops,
                        "step_frac_bf16_peak": step_tflops / peaks["bf16"],
