@@ -42,4 +42,4 @@ def time_port_stripe(pairs_global: int, dim: int, tau: float, b_sample: int, ste
             times.append(dt)
     mean = sum(times) / len(times)
     return dict(pairs_per_s=b_sample / mean, s_per_step=mean, b_sample=b_sample, threads=threads,
-                loss=float(loss), steps=steps, warmup=warmup)
+                loss=float(loss.detach()), steps=steps, warmup=warmup)
