@@ -613,8 +613,11 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const uint32_t lane_base = tmem_base + (uint32_t(w4 * 32) << 16) + col_off;
     const float c1 = p.c1;
     const float kscale = ex2_approx(-c1);  // 2^-c1: what the polynomial path leaves out
-    constexpr int POLY_A = BWD ? MAAI_POLY_BWD : MAAI_POLY_FWD;
-    constexpr int POLY_B = BWD ? MAAI_POLY_BWD_B : MAAI_POLY_FWD_B;
+    // backward at d_pad = 64: the MMAs are half as long, MUFU is the top pipe -> 2 of 8 pairs on the
+    // polynomial (1.345 -> 1.301 ms at 32768 pairs); at 128 / 256 the split makes no difference
+    constexpr int POLY_BWD_D = (D == 64 && MAAI_POLY_BWD == 0) ? 2 : MAAI_POLY_BWD;
+    constexpr int POLY_A = BWD ? POLY_BWD_D : MAAI_POLY_FWD;
+    constexpr int POLY_B = BWD ? ((MAAI_POLY_BWD_B == MAAI_POLY_BWD) ? POLY_BWD_D : MAAI_POLY_BWD_B) : MAAI_POLY_FWD_B;
     constexpr int DEG = BWD ? MAAI_POLY_DEG_BWD : MAAI_POLY_DEG_FWD;
     // Running ring positions of the next S tile of this warp (kept incrementally: no div / mod
     // in the per-tile path): S buffer slot + phase, K stage + phase.
