@@ -390,6 +390,8 @@ def main():
                        "l2": "flushed between timed steps (256 MiB write outside the event bracket)",
                        "step_tflops_per_gpu_algorithmic": step_tflops,
                        "step_frac_bf16_peak": step_tflops / peaks["bf16"],
+                       # executed flops: a single rank runs the symmetric forward (half the forward's MMAs)
+                       "step_tflops_per_gpu_executed": step_tflops * ((20.0 / 24.0) if (world == 1 and maai_b200.padded_dim(d) <= 128) else 1.0),
                        "ms_median": main_r["ms_median"], "loss": main_r["loss"],
                        "fwd_call_ms": fwd_ms, "bwd_call_ms": bwd_ms,
                        "span_ms_mean": {k: (statistics.mean(v) if v else None) for k, v in main_r["spans"].items()}},
