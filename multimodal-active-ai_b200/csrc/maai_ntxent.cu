@@ -160,7 +160,7 @@ int launch_tile(const void* q_base, int m_loc, const void* k_base, int m_glob, i
   static const uint32_t pv_sbo = getenv("MAAI_DEBUG_PV_SBO") ? atoi(getenv("MAAI_DEBUG_PV_SBO")) : 1024;
   p.pv_lbo = pv_lbo;
   p.pv_sbo = pv_sbo;
-  const long long items = SYM ? (long long)p.nrb * p.nkt - (long long)p.nrb * (p.nrb - 1)
+  const long long items = SYM ? (long long)p.nrb * p.nkt - (long long)NQ * p.nrb * (p.nrb - 1) / 2
                               : (long long)p.nrb * p.nkt;
   int sms = sm_count();
   if (sms <= 0) return fail(MAAI_E_CUDA, "no CUDA device");
@@ -290,8 +290,7 @@ static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, f
       default: return fail(MAAI_E_SHAPE, "d_pad must be 64, 128 or 256");
     }
 #undef MAAI_LAUNCH_RANK
-  } else if (world == 1 && (d_pad == 64 || d_pad == 128) && env_int("MAAI_DEBUG_FWD_NQ", 2) == 2 &&
-             env_int("MAAI_FWD_SYM", 1) != 0) {
+  } else if (world == 1 && env_int("MAAI_DEBUG_FWD_NQ", 2) == 2 && env_int("MAAI_FWD_SYM", 1) != 0) {
     // Single rank: anchors == keys and E_ij = E_ji, so only the tiles on and above the diagonal are
     // computed; a tile above it adds its row sums to the anchors and its column sums to the keys
     // (half the MMAs and exp2s; measured forward 0.955 -> 0.724 ms at 32768 pairs, d=128, 0.884 -> 0.726
@@ -299,8 +298,11 @@ static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, f
     if (d_pad == 64)
       rc = launch_tile<64, false, 2, false, true>(q_base, m_loc, z_glob, m_glob, 0, inv_tau, nullptr, nullptr,
                                                   rowsum_l, nullptr, b, b, s);
-    else
+    else if (d_pad == 128)
       rc = launch_tile<128, false, 2, false, true>(q_base, m_loc, z_glob, m_glob, 0, inv_tau, nullptr, nullptr,
+                                                   rowsum_l, nullptr, b, b, s);
+    else  // one Q tile per row block: row tile rb visits key tiles kt >= rb
+      rc = launch_tile<256, false, 1, false, true>(q_base, m_loc, z_glob, m_glob, 0, inv_tau, nullptr, nullptr,
                                                    rowsum_l, nullptr, b, b, s);
   } else {
     rc = dispatch_tile<false>(d_pad, q_base, m_loc, z_glob, m_glob, rank * m_loc, inv_tau, nullptr,

@@ -307,13 +307,13 @@ __device__ __forceinline__ void softmax_chunk(uint32_t (&v)[CW], uint32_t (&pk)[
 // row block).  SYM (symmetric forward, anchors == keys): row block rb only visits key tiles
 // kt >= 2*rb, because E_ij = E_ji lets every tile above the diagonal contribute its row sums to the
 // anchors AND its column sums to the keys; the tiles below the diagonal are never computed.
-template <bool SYM>
+template <bool SYM, int NQ>
 struct SegWalk {
   int nkt;
   int rb = 0;
   long long cum = 0;  // items before row block rb
   __device__ __forceinline__ explicit SegWalk(int nkt_) : nkt(nkt_) {}
-  __device__ __forceinline__ int cnt(int r) const { return SYM ? nkt - 2 * r : nkt; }
+  __device__ __forceinline__ int cnt(int r) const { return SYM ? nkt - NQ * r : nkt; }
   // segment that starts at item `it`: row block, first key tile, number of key tiles
   __device__ __forceinline__ void locate(long long it, long long it_end, int& rb_out, int& j0, int& n) {
     if (SYM) {
@@ -323,7 +323,7 @@ struct SegWalk {
       }
       const int off = int(it - cum);
       rb_out = rb;
-      j0 = 2 * rb + off;
+      j0 = NQ * rb + off;
       n = int(min((long long)(cnt(rb) - off), it_end - it));
     } else {
       rb_out = int(it / nkt);
@@ -365,9 +365,10 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
   pdl_launch_dependents<4>();
 
   // ---- this CTA's contiguous range of (row block, key tile) items ----
-  static_assert(!SYM || (!BWD && !RANK && NQ == 2 && MAAI_FWD_CW == 32),
-                "symmetric mode: plain forward, two Q tiles per row block, 32-column chunks");
-  const long long total = SYM ? (long long)p.nrb * p.nkt - (long long)p.nrb * (p.nrb - 1)
+  static_assert(!SYM || (!BWD && !RANK && MAAI_FWD_CW == 32 && (NQ == 2 || MAAI_NQ1_TEAMS == 2)),
+                "symmetric mode: plain forward, 64 columns per softmax thread in 32-column chunks");
+  // sum over rb of (nkt - NQ rb)
+  const long long total = SYM ? (long long)p.nrb * p.nkt - (long long)NQ * p.nrb * (p.nrb - 1) / 2
                               : (long long)p.nrb * p.nkt;
   const long long it_begin = total * blockIdx.x / gridDim.x;
   const long long it_end = total * (blockIdx.x + 1) / gridDim.x;
@@ -409,7 +410,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
     if (lane == 0) {
       PROF_INIT();
       uint32_t t = 0, useg = 0;
-      SegWalk<SYM> walk(p.nkt);
+      SegWalk<SYM, NQ> walk(p.nkt);
       for (long long it = it_begin; it < it_end;) {
         int rb, j0, n;
         walk.locate(it, it_end, rb, j0, n);
@@ -517,7 +518,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       PROF_MARK(3);
     };
 
-    SegWalk<SYM> walk(p.nkt);
+    SegWalk<SYM, NQ> walk(p.nkt);
     uint32_t symu[2] = {0, 0};  // SYM: S tiles issued so far per team (a team skips tiles below the diagonal)
 #pragma unroll 1
     for (long long it = it_begin; it < it_end;) {
@@ -540,7 +541,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
         issue_s(sg0 + s, q, st);
       };
-      if (!BWD && SYM) {
+      if (!BWD && SYM && NQ == 2) {
 #pragma unroll 1
         for (int jj = 0; jj < n; ++jj) {
           const uint32_t tk = t + jj;
@@ -639,7 +640,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
     for (int i = 0; i < 8; ++i) cx.prof_a[i] = 0;
 #endif
 
-    SegWalk<SYM> walk(p.nkt);
+    SegWalk<SYM, NQ> walk(p.nkt);
     // SYM: partial row sums of the tiles above the diagonal, in the 16x256b fragment layout: slot k of
     // a thread is tile row 32 w4 + 8 k + lane / 4 (k = 0..3), summed over the thread's columns
     float2 racc_m[4], racc_p[4];
@@ -681,8 +682,8 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const int kt = j0 + jj;
         // SYM: key tile kt against row tile 2 rb + q: below the diagonal -> not computed at all,
         // on it -> ordinary tile (row sums), above it -> row sums AND column sums
-        if (SYM && kt < 2 * rb + q) continue;
-        const bool upper = SYM && kt > 2 * rb + q;
+        if (SYM && kt < NQ * rb + q) continue;
+        const bool upper = SYM && kt > NQ * rb + q;
         const int buf = (NQ == 2) ? team * MODB + sb : sb;
         const bool special = unsigned(kt - kt_d) <= 1u || unsigned(kt - kt_p1) <= 1u ||
                              unsigned(kt - kt_p2) <= 1u || kt == kt_ragged;
