@@ -290,7 +290,11 @@ static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, f
       default: return fail(MAAI_E_SHAPE, "d_pad must be 64, 128 or 256");
     }
 #undef MAAI_LAUNCH_RANK
-  } else if (world == 1 && env_int("MAAI_DEBUG_FWD_NQ", 2) == 2 && env_int("MAAI_FWD_SYM", 1) != 0) {
+  } else if (world == 1 && env_int("MAAI_DEBUG_FWD_NQ", 2) == 2 &&
+             (env_int("MAAI_FWD_SYM", -1) == 1 ||
+              // d_pad = 256 below 8192 pairs: the triangular item list cuts a CTA's range into several short
+              // segments, each with its own 64 KB Q-tile load (measured 0.17 -> 0.27 ms per step at 4096 pairs)
+              (env_int("MAAI_FWD_SYM", -1) == -1 && (d_pad <= 128 || m_loc >= 16384)))) {
     // Single rank: anchors == keys and E_ij = E_ji, so only the tiles on and above the diagonal are
     // computed; a tile above it adds its row sums to the anchors and its column sums to the keys
     // (half the MMAs and exp2s; measured forward 0.955 -> 0.724 ms at 32768 pairs, d=128, 0.884 -> 0.726
