@@ -352,6 +352,19 @@ def main():
         detached = {"workload": workload_name(B, d, tau).replace("both inputs require grad", "hidden1 detached (training call)"),
                     "ms_per_step": s2["ms_per_step"], "pairs_per_s": B / (s2["ms_per_step"] * 1e-3)}
 
+    # ---------------- secondary: configs[0] (256 pairs, the reference's own CPU-runnable case) ----------------
+    configs0 = None
+    if rank == 0 and world == 1 and not args.no_secondary and not args.no_cpu_baseline:
+        from oracle.cpu_baseline import time_port_full
+        s0 = timed_run(256, max(args.steps, 100), args.warmup, profile=False)
+        c0 = time_port_full(256, d, tau, steps=30, warmup=5)
+        configs0 = {"workload": workload_name(256, d, tau), "ms_per_step": s0["ms_per_step"],
+                    "pairs_per_s": 256 / (s0["ms_per_step"] * 1e-3), "loss": s0["loss"],
+                    "cpu_reference_port": {"ms_per_step": c0["s_per_step"] * 1e3, "pairs_per_s": c0["pairs_per_s"],
+                                           "cores": c0["threads"], "loss": c0["loss"]},
+                    "note": "host-launch-bound on the GPU (9 launches from Python per step); different random "
+                            "draws on the two devices, parity at this shape is tests/test_gpu_parity.py"}
+
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -423,6 +436,8 @@ def main():
             line["config"]["configs1_4096_pairs"] = secondary
         if detached:
             line["config"]["hidden1_detached"] = detached
+        if configs0:
+            line["config"]["configs0_256_pairs"] = configs0
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -43,3 +43,27 @@ def time_port_stripe(pairs_global: int, dim: int, tau: float, b_sample: int, ste
     mean = sum(times) / len(times)
     return dict(pairs_per_s=b_sample / mean, s_per_step=mean, b_sample=b_sample, threads=threads,
                 loss=float(loss.detach()), steps=steps, warmup=warmup)
+
+
+def time_port_full(pairs: int, dim: int, tau: float, steps: int, warmup: int, threads: int | None = None,
+                   seed: int = 1234):
+    """The reference's single-process call on a WHOLE (small) batch, forward + backward, both inputs
+    requiring grad (BASELINE.json configs[0]: 256 pairs, d=128, tau=0.5 on CPU)."""
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(pairs, dim, generator=g).requires_grad_(True)
+    y = torch.randn(pairs, dim, generator=g).requires_grad_(True)
+    times = []
+    for i in range(warmup + steps):
+        x.grad = None
+        y.grad = None
+        t0 = time.perf_counter()
+        loss = ntxent_port(x, y, tau)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    times.sort()
+    med = times[len(times) // 2]
+    return dict(pairs_per_s=pairs / med, s_per_step=med, threads=threads, loss=float(loss.detach()))
