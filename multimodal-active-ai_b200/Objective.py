@@ -160,11 +160,16 @@ class PeerWorkspace:
         torch.cuda.synchronize(device)
         self.hdl.barrier(channel=0)                      # every rank's zero fill is done before first use
 
+    MAX_CACHED = 4  # shapes kept alive (symmetric memory is not returned to the caching allocator)
+
     @classmethod
     def get(cls, b, dp, world, rank, device, group):
         key = (b, dp, world, rank, str(device), id(group))
         ws = cls._cache.get(key)
         if ws is None:
+            # every rank sees the same sequence of shapes, so they evict the same (oldest) entry
+            while len(cls._cache) >= cls.MAX_CACHED:
+                cls._cache.pop(next(iter(cls._cache)))
             ws = cls._cache[key] = cls(b, dp, world, rank, device, group)
         return ws
 
