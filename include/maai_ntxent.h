@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MAAI_ABI_VERSION 3
+#define MAAI_ABI_VERSION 4
 
 #define MAAI_OK 0
 #define MAAI_E_ARG (-1)
@@ -120,6 +120,30 @@ int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, 
                     const float* rowsum_l, const float* pos_cos, const void* h1, const void* h2, int in_dtype,
                     const float* inv_norm, const float* grad_loss, int b, int world, int rank, int d, int d_pad,
                     float inv_tau, int need_mask, void* dh1, void* dh2, float* dz_acc, void* stream);
+
+/* The backward in its three pieces, for the key-side REDUCE-SCATTER dataflow (SURVEY.md section 7 /
+ * BASELINE.json north_star): instead of using the symmetry of E (maai_ntxent_bwd, key_grad = 1), every
+ * rank computes, for the anchors of ALL ranks, the key-side sums over ITS OWN keys, and a
+ * reduce_scatter(sum) of the (world*2b, d_pad) fp32 result delivers each rank its rows:
+ *   maai_ntxent_bwd_keyside : dz_keys[i] = sum_{j in this rank's slot, j != i, pos(i)} E_ij r_j z_j   (all i)
+ *   <reduce_scatter of dz_keys over the ranks, e.g. torch.distributed.reduce_scatter_tensor>
+ *   maai_ntxent_bwd_tiles   : dz_acc[i]  = sum_{j != i, pos(i)} E_ij (r_row_i + r_col_j) z_j  (this rank's i;
+ *                             the first half of maai_ntxent_bwd; pass r_col = zeros for the query side only)
+ *   maai_ntxent_bwd_dh      : dh from dz_acc + dz_extra (the reduce-scattered rows, or NULL) -- the second
+ *                             half of maai_ntxent_bwd; key_grad = 1 keeps the key-side term of the positive.
+ * Both dataflows give the same gradient (tests/test_gpu_multirank.py); the identity form needs no
+ * gradient collective and 2/3 of the tensor-core work, and is the default.
+ *   r_col_loc  maai_ntxent_r_len(b, 1) floats: this rank's r_out, zero padded
+ *   dz_keys    (world*2b, d_pad) fp32 out, zeroed inside
+ *   dz_extra   (2b, d_pad) fp32 or NULL */
+int maai_ntxent_bwd_tiles(const void* z_glob, const float* r_row, const float* r_col, int b, int world, int rank,
+                          int d_pad, float inv_tau, int need_mask, float* dz_acc, void* stream);
+int maai_ntxent_bwd_keyside(const void* z_glob, const float* r_col_loc, int b, int world, int rank, int d_pad,
+                            float inv_tau, float* dz_keys, void* stream);
+int maai_ntxent_bwd_dh(const float* dz_acc, const float* dz_extra, const float* rowsum_l, const float* pos_cos,
+                       const void* h1, const void* h2, int in_dtype, const float* inv_norm,
+                       const float* grad_loss, int b, int d, int d_pad, float inv_tau, int key_grad, int need_mask,
+                       void* dh1, void* dh2, void* stream);
 
 /* Kernel launches enqueued by this library since load (bench.py's gpu_launches claim). */
 unsigned long long maai_launch_count(void);

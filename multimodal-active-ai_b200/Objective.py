@@ -242,7 +242,12 @@ class _NTXentFunction(torch.autograd.Function):
         inv_tau = 1.0 / float(temperature)
 
         needs_grad = any(ctx.needs_input_grad[:2])
-        full = bool(key_grad) or world == 1
+        # key_grad="reduce_scatter": full gradient through the key-side reduce-scatter dataflow
+        # (backward below); the forward then needs no gather of the row factors at all
+        rs = key_grad == "reduce_scatter" and world > 1
+        full = (bool(key_grad) and not rs) or world == 1
+        ctx.rs_group = group if rs else None
+        ctx.rs = rs
         if peer and world > 1:
             return _NTXentFunction._forward_peer(ctx, h1, h2, dt, inv_tau, rank, world, group, needs_grad, full,
                                                  stash)
@@ -350,6 +355,8 @@ class _NTXentFunction(torch.autograd.Function):
         dh1 = torch.empty_like(h1) if need & 1 else None
         dh2 = torch.empty_like(h2) if need & 2 else None
         dz_acc = torch.empty((2 * b, dp), dtype=torch.float32, device=dev)
+        if ctx.rs:
+            return _NTXentFunction._backward_reduce_scatter(ctx, g, need, dh1, dh2, dz_acc)
         with _Profiler.span("bwd"):
             _lib.check(lib.maai_ntxent_bwd(_ptr(z_all), _ptr(r_row), _ptr(r_col), 1 if full else 0,
                                            _ptr(rowsum), _ptr(pos_cos), _ptr(h1), _ptr(h2), dt, _ptr(inv_norm),
@@ -357,6 +364,37 @@ class _NTXentFunction(torch.autograd.Function):
                                            _ptr(dh2), _ptr(dz_acc), _stream()),
                        "maai_ntxent_bwd")
         return dh1, dh2, None, None, None, None, None, None, None
+
+
+def _backward_reduce_scatter(ctx, g, need, dh1, dh2, dz_acc):
+    """Full gradient by the dataflow SURVEY.md section 7 names: key-side partial sums of every rank's
+    anchors over the local keys -> reduce_scatter(sum) -> local rows; the query-side tile pass runs
+    while the collective is in flight.  Every rank must call backward with the same need mask."""
+    lib = _lib.load()
+    h1, h2, z_all, inv_norm, r_row, r_col, pos_cos, rowsum = ctx.saved_tensors
+    b, d, dp, dt, inv_tau, rank, world, _ = ctx.cfg
+    dev = h1.device
+    r_pad = torch.zeros(lib.maai_ntxent_r_len(b, 1), dtype=torch.float32, device=dev)
+    r_pad[:2 * b].copy_(r_row)
+    dz_keys = torch.empty((world * 2 * b, dp), dtype=torch.float32, device=dev)
+    dz_mine = torch.empty((2 * b, dp), dtype=torch.float32, device=dev)
+    with _Profiler.span("bwd_keyside"):
+        _lib.check(lib.maai_ntxent_bwd_keyside(_ptr(z_all), _ptr(r_pad), b, world, rank, dp, inv_tau,
+                                               _ptr(dz_keys), _stream()), "maai_ntxent_bwd_keyside")
+    work = dist.reduce_scatter_tensor(dz_mine, dz_keys, group=ctx.rs_group, async_op=True)
+    with _Profiler.span("bwd"):
+        _lib.check(lib.maai_ntxent_bwd_tiles(_ptr(z_all), _ptr(r_row), _ptr(r_col), b, world, rank, dp, inv_tau,
+                                             need, _ptr(dz_acc), _stream()), "maai_ntxent_bwd_tiles")
+    with _Profiler.span("reduce_scatter_wait"):
+        work.wait()
+    with _Profiler.span("bwd_dh"):
+        _lib.check(lib.maai_ntxent_bwd_dh(_ptr(dz_acc), _ptr(dz_mine), _ptr(rowsum), _ptr(pos_cos), _ptr(h1),
+                                          _ptr(h2), dt, _ptr(inv_norm), _ptr(g), b, d, dp, inv_tau, 1, need,
+                                          _ptr(dh1), _ptr(dh2), _stream()), "maai_ntxent_bwd_dh")
+    return dh1, dh2, None, None, None, None, None, None, None
+
+
+_NTXentFunction._backward_reduce_scatter = staticmethod(_backward_reduce_scatter)
 
 
 def _forward_eval(hidden1, hidden2, temperature, rank, world, group):
@@ -413,7 +451,10 @@ def contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0, local_
 
     Args (reference): hidden1, hidden2 (bsz, dim); hidden_norm; temperature; local_rank (really the
       global rank, Contrastive_Learning.py:688); world_size; device (ignored: the tensors' device).
-    Extra keyword-only args: ``group`` process group for the gathers; ``key_grad`` see module doc;
+    Extra keyword-only args: ``group`` process group for the gathers; ``key_grad`` see module doc
+      (True: full gradient via the symmetry of E, no gradient collective; False: the reference's
+      query-side-only gradient; "reduce_scatter": the same full gradient computed as key-side partial
+      sums + ``dist.reduce_scatter_tensor`` -- kept for comparison, 1.5x the tensor-core work);
       ``return_logits`` force (True) / suppress (False) the (logits_ab, labels) outputs, default:
       only when autograd is disabled (the validate() path).
       ``peer_gather`` (world_size > 1): True = the two gathers of the path are fused into the producing

@@ -122,6 +122,8 @@ int sm_count() {
 struct RankArgs {
   const float* pos_cos = nullptr;
   int* rank_out = nullptr;
+  int pos_period = 0;  // anchors spanning several rank slots (maai_ntxent_bwd_tiles)
+  int pos_phase = 0;
 };
 
 template <int D, bool BWD, int NQ, bool RANK = false, bool SYM = false>
@@ -146,6 +148,8 @@ int launch_tile(const void* q_base, int m_loc, const void* k_base, int m_glob, i
   p.row_global_base = row_global_base;
   p.pos_split = pos_split;
   p.pos_delta = pos_delta;
+  p.pos_period = ra.pos_period;
+  p.pos_phase = ra.pos_phase;
   p.nrb = (m_loc + C::RB_ROWS - 1) / C::RB_ROWS;
   p.nkt = (m_glob + C::KT - 1) / C::KT;
   p.c1 = inv_tau * 1.4426950408889634f;
@@ -181,11 +185,12 @@ int env_int(const char* name, int dflt) {
 template <bool BWD>
 int dispatch_tile(int d_pad, const void* q_base, int m_loc, const void* k_base, int m_glob,
                   int row_global_base, float inv_tau, const float* r_row, const float* r_col,
-                  float* l_out, float* dz_acc, int pos_split, int pos_delta, cudaStream_t s) {
+                  float* l_out, float* dz_acc, int pos_split, int pos_delta, cudaStream_t s,
+                  RankArgs ra = RankArgs()) {
   static const int nq = BWD ? env_int("MAAI_DEBUG_BWD_NQ", 1) : env_int("MAAI_DEBUG_FWD_NQ", 2);
 #define MAAI_LAUNCH(DD, NQQ)                                                                       \
   return launch_tile<DD, BWD, NQQ>(q_base, m_loc, k_base, m_glob, row_global_base, inv_tau, r_row, \
-                                   r_col, l_out, dz_acc, pos_split, pos_delta, s)
+                                   r_col, l_out, dz_acc, pos_split, pos_delta, s, ra)
   switch (d_pad) {
     case 64:
       if (nq == 2) MAAI_LAUNCH(64, 2);
@@ -377,58 +382,128 @@ int maai_ntxent_fwd_eval(const void* z_glob, int b, int world, int rank, int d_p
                   stream);
 }
 
-int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, int key_grad,
-                    const float* rowsum_l, const float* pos_cos, const void* h1, const void* h2, int in_dtype,
-                    const float* inv_norm, const float* grad_loss, int b, int world, int rank, int d, int d_pad,
-                    float inv_tau, int need_mask, void* dh1, void* dh2, float* dz_acc, void* stream) {
-  if (!z_glob || !r_row || !r_col || !rowsum_l || !pos_cos || !h1 || !h2 || !inv_norm || !grad_loss || !dz_acc)
-    return fail(MAAI_E_ARG, "null pointer");
-  int rc = check_common(b, world, rank);
-  if (rc != MAAI_OK) return rc;
-  if (need_mask < 0 || need_mask > 3) return fail(MAAI_E_ARG, "need_mask must be in [0, 3]");
-  if (need_mask == 0) return MAAI_OK;
-  if (((need_mask & 1) && !dh1) || ((need_mask & 2) && !dh2)) return fail(MAAI_E_ARG, "null dh");
-  if (maai_padded_dim(d) != d_pad) return fail(MAAI_E_SHAPE, "d_pad does not match maai_padded_dim(d)");
-  if (!aligned16(z_glob) || !aligned16(r_col) || !aligned16(dz_acc))
-    return fail(MAAI_E_ARG, "z_glob, r_col and dz_acc must be 16-byte aligned");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+// tile pass of the backward over this rank's anchors: zeroes the accumulator rows, then K3
+static int bwd_tiles_impl(const void* z_glob, const float* r_row, const float* r_col, int b, int world, int rank,
+                          int d_pad, float inv_tau, int need_mask, float* dz_acc, cudaStream_t s) {
   const int m_loc = 2 * b, m_glob = 2 * b * world;
   // anchor rows that need a gradient: both views, or one contiguous view
   const int row_begin = (need_mask == 2) ? b : 0;
   const int rows = (need_mask == 3) ? m_loc : b;
   float* acc = dz_acc + (size_t)row_begin * d_pad;
+  int rc;
   if ((rc = zero_words(acc, (size_t)rows * d_pad, s)) != MAAI_OK) return rc;
   const char* q_base =
       static_cast<const char*>(z_glob) + ((size_t)rank * m_loc + row_begin) * d_pad * 2;
-  rc = dispatch_tile<true>(d_pad, q_base, rows, z_glob, m_glob, rank * m_loc + row_begin, inv_tau,
-                           r_row + row_begin, r_col, nullptr, acc, b - row_begin, b, s);
-  if (rc != MAAI_OK) return rc;
+  return dispatch_tile<true>(d_pad, q_base, rows, z_glob, m_glob, rank * m_loc + row_begin, inv_tau,
+                             r_row + row_begin, r_col, nullptr, acc, b - row_begin, b, s);
+}
+
+static int bwd_dh_impl(const float* dz_acc, const float* dz_extra, const float* rowsum_l, const float* pos_cos,
+                       const void* h1, const void* h2, int in_dtype, const float* inv_norm,
+                       const float* grad_loss, int b, int d, int d_pad, float inv_tau, int key_grad,
+                       int need_mask, void* dh1, void* dh2, cudaStream_t s) {
+  const int rows = (need_mask == 3) ? 2 * b : b;
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
-  const float* dza = dz_acc;
   cudaError_t e;
   switch (in_dtype) {
     case MAAI_DT_F32:
-      e = launch_k(maai::dh_kernel<float>, dim3(grid), dim3(wpb * 32), 0, s, dza, static_cast<const float*>(h1),
-                   static_cast<const float*>(h2), inv_norm, grad_loss, rowsum_l, pos_cos, b, d, d_pad, inv_tau,
-                   key_grad, need_mask, static_cast<float*>(dh1), static_cast<float*>(dh2));
+      e = launch_k(maai::dh_kernel<float>, dim3(grid), dim3(wpb * 32), 0, s, dz_acc, dz_extra,
+                   static_cast<const float*>(h1), static_cast<const float*>(h2), inv_norm, grad_loss, rowsum_l,
+                   pos_cos, b, d, d_pad, inv_tau, key_grad, need_mask, static_cast<float*>(dh1),
+                   static_cast<float*>(dh2));
       break;
     case MAAI_DT_BF16:
-      e = launch_k(maai::dh_kernel<__nv_bfloat16>, dim3(grid), dim3(wpb * 32), 0, s, dza,
+      e = launch_k(maai::dh_kernel<__nv_bfloat16>, dim3(grid), dim3(wpb * 32), 0, s, dz_acc, dz_extra,
                    static_cast<const __nv_bfloat16*>(h1), static_cast<const __nv_bfloat16*>(h2), inv_norm, grad_loss,
                    rowsum_l, pos_cos, b, d, d_pad, inv_tau, key_grad, need_mask, static_cast<__nv_bfloat16*>(dh1),
                    static_cast<__nv_bfloat16*>(dh2));
       break;
     case MAAI_DT_F16:
-      e = launch_k(maai::dh_kernel<__half>, dim3(grid), dim3(wpb * 32), 0, s, dza, static_cast<const __half*>(h1),
-                   static_cast<const __half*>(h2), inv_norm, grad_loss, rowsum_l, pos_cos, b, d, d_pad, inv_tau,
-                   key_grad, need_mask, static_cast<__half*>(dh1), static_cast<__half*>(dh2));
+      e = launch_k(maai::dh_kernel<__half>, dim3(grid), dim3(wpb * 32), 0, s, dz_acc, dz_extra,
+                   static_cast<const __half*>(h1), static_cast<const __half*>(h2), inv_norm, grad_loss, rowsum_l,
+                   pos_cos, b, d, d_pad, inv_tau, key_grad, need_mask, static_cast<__half*>(dh1),
+                   static_cast<__half*>(dh2));
       break;
     default:
       return fail(MAAI_E_ARG, "in_dtype must be MAAI_DT_F32, MAAI_DT_BF16 or MAAI_DT_F16");
   }
   MAAI_CUDA(e);
   return MAAI_OK;
+}
+
+static int bwd_check(int b, int world, int rank, int d, int d_pad, int need_mask) {
+  int rc = check_common(b, world, rank);
+  if (rc != MAAI_OK) return rc;
+  if (need_mask < 0 || need_mask > 3) return fail(MAAI_E_ARG, "need_mask must be in [0, 3]");
+  if (d > 0 && maai_padded_dim(d) != d_pad) return fail(MAAI_E_SHAPE, "d_pad does not match maai_padded_dim(d)");
+  if (d_pad != 64 && d_pad != 128 && d_pad != 256) return fail(MAAI_E_SHAPE, "d_pad must be 64, 128 or 256");
+  return MAAI_OK;
+}
+
+int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, int key_grad,
+                    const float* rowsum_l, const float* pos_cos, const void* h1, const void* h2, int in_dtype,
+                    const float* inv_norm, const float* grad_loss, int b, int world, int rank, int d, int d_pad,
+                    float inv_tau, int need_mask, void* dh1, void* dh2, float* dz_acc, void* stream) {
+  if (!z_glob || !r_row || !r_col || !rowsum_l || !pos_cos || !h1 || !h2 || !inv_norm || !grad_loss || !dz_acc)
+    return fail(MAAI_E_ARG, "null pointer");
+  int rc = bwd_check(b, world, rank, d, d_pad, need_mask);
+  if (rc != MAAI_OK) return rc;
+  if (need_mask == 0) return MAAI_OK;
+  if (((need_mask & 1) && !dh1) || ((need_mask & 2) && !dh2)) return fail(MAAI_E_ARG, "null dh");
+  if (!aligned16(z_glob) || !aligned16(r_col) || !aligned16(dz_acc))
+    return fail(MAAI_E_ARG, "z_glob, r_col and dz_acc must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if ((rc = bwd_tiles_impl(z_glob, r_row, r_col, b, world, rank, d_pad, inv_tau, need_mask, dz_acc, s)) != MAAI_OK)
+    return rc;
+  return bwd_dh_impl(dz_acc, nullptr, rowsum_l, pos_cos, h1, h2, in_dtype, inv_norm, grad_loss, b, d, d_pad,
+                     inv_tau, key_grad, need_mask, dh1, dh2, s);
+}
+
+int maai_ntxent_bwd_tiles(const void* z_glob, const float* r_row, const float* r_col, int b, int world, int rank,
+                          int d_pad, float inv_tau, int need_mask, float* dz_acc, void* stream) {
+  if (!z_glob || !r_row || !r_col || !dz_acc) return fail(MAAI_E_ARG, "null pointer");
+  int rc = bwd_check(b, world, rank, 0, d_pad, need_mask);
+  if (rc != MAAI_OK) return rc;
+  if (need_mask == 0) return MAAI_OK;
+  if (!aligned16(z_glob) || !aligned16(r_col) || !aligned16(dz_acc))
+    return fail(MAAI_E_ARG, "z_glob, r_col and dz_acc must be 16-byte aligned");
+  return bwd_tiles_impl(z_glob, r_row, r_col, b, world, rank, d_pad, inv_tau, need_mask, dz_acc,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int maai_ntxent_bwd_keyside(const void* z_glob, const float* r_col_loc, int b, int world, int rank, int d_pad,
+                            float inv_tau, float* dz_keys, void* stream) {
+  if (!z_glob || !r_col_loc || !dz_keys) return fail(MAAI_E_ARG, "null pointer");
+  int rc = bwd_check(b, world, rank, 0, d_pad, 3);
+  if (rc != MAAI_OK) return rc;
+  if (!aligned16(z_glob) || !aligned16(r_col_loc) || !aligned16(dz_keys))
+    return fail(MAAI_E_ARG, "z_glob, r_col_loc and dz_keys must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int m_loc = 2 * b, m_glob = 2 * b * world;
+  if ((rc = zero_words(dz_keys, (size_t)m_glob * d_pad, s)) != MAAI_OK) return rc;
+  // anchors: every row of the gathered buffer; keys: this rank's slot.  In key space (0 = first key
+  // of the slot) anchor row 0 sits at -rank*2b; the view of an anchor follows from its slot offset.
+  const char* k_base = static_cast<const char*>(z_glob) + (size_t)rank * m_loc * d_pad * 2;
+  RankArgs ra;
+  ra.pos_period = m_loc;
+  ra.pos_phase = 0;
+  return dispatch_tile<true>(d_pad, z_glob, m_glob, k_base, m_loc, -rank * m_loc, inv_tau, nullptr, r_col_loc,
+                             nullptr, dz_keys, 0, b, s, ra);
+}
+
+int maai_ntxent_bwd_dh(const float* dz_acc, const float* dz_extra, const float* rowsum_l, const float* pos_cos,
+                       const void* h1, const void* h2, int in_dtype, const float* inv_norm,
+                       const float* grad_loss, int b, int d, int d_pad, float inv_tau, int key_grad, int need_mask,
+                       void* dh1, void* dh2, void* stream) {
+  if (!dz_acc || !rowsum_l || !pos_cos || !h1 || !h2 || !inv_norm || !grad_loss)
+    return fail(MAAI_E_ARG, "null pointer");
+  int rc = bwd_check(b, 1, 0, d, d_pad, need_mask);
+  if (rc != MAAI_OK) return rc;
+  if (need_mask == 0) return MAAI_OK;
+  if (((need_mask & 1) && !dh1) || ((need_mask & 2) && !dh2)) return fail(MAAI_E_ARG, "null dh");
+  return bwd_dh_impl(dz_acc, dz_extra, rowsum_l, pos_cos, h1, h2, in_dtype, inv_norm, grad_loss, b, d, d_pad,
+                     inv_tau, key_grad, need_mask, dh1, dh2, static_cast<cudaStream_t>(stream));
 }
 
 #if MAAI_PROF

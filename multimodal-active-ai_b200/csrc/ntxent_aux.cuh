@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256) zero_kernel(uint32_t* __restrict__ p, siz
 }
 
 // One warp per anchor row i of the views that need a gradient.
-//   dz_i = (g / tau) * (A_i + cpos_i z_pos(i)),  A = dz_acc (fp32, stride dp, positive column excluded)
+//   dz_i = (g / tau) * (A_i + cpos_i z_pos(i)),  A = dz_acc (+ dz_extra) (fp32, stride dp, positive column excluded)
 //   cpos_i = [e_pos/(e_pos + l'_i) - 1]/b  (+ the same with l'_pos when the key side is kept)
 //          = -(1/b) [ l'_i/(e_pos + l'_i) + key_grad * l'_pos/(e_pos + l'_pos) ]
 // i.e. the positive pair's softmax-minus-target coefficient without any cancellation.
@@ -235,7 +235,8 @@ __global__ void __launch_bounds__(256) zero_kernel(uint32_t* __restrict__ p, siz
 // z_i, z_pos are recomputed in fp32 from h (not the bf16 copies).
 template <typename T>
 __global__ void __launch_bounds__(256)
-dh_kernel(const float* __restrict__ dz_acc, const T* __restrict__ h1, const T* __restrict__ h2,
+dh_kernel(const float* __restrict__ dz_acc, const float* __restrict__ dz_extra, const T* __restrict__ h1,
+          const T* __restrict__ h2,
           const float* __restrict__ inv_norm, const float* __restrict__ grad_loss,
           const float* __restrict__ lneg, const float* __restrict__ pos_cos, int b, int d, int dp,
           float inv_tau, int key_grad, int need_mask, T* __restrict__ dh1, T* __restrict__ dh2) {
@@ -268,7 +269,9 @@ dh_kernel(const float* __restrict__ dz_acc, const T* __restrict__ h1, const T* _
     if (e < d) {
       z[j] = to_f32<T>(hi[e]) * inv_i;
       const float zp = to_f32<T>(hp[e]) * inv_p;
-      dz[j] = gs * (dz_acc[(size_t)i * dp + e] + cpos * zp);
+      float a = dz_acc[(size_t)i * dp + e];
+      if (dz_extra) a += dz_extra[(size_t)i * dp + e];  // key-side sums that arrived by reduce-scatter
+      dz[j] = gs * (a + cpos * zp);
       dot += z[j] * dz[j];
     } else {
       z[j] = 0.f;

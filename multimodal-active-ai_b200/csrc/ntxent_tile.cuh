@@ -135,10 +135,12 @@ struct TileParams {
   int row_global_base;   // global (key-space) index of anchor row 0
   int pos_split;         // anchor rows < pos_split have their positive at +pos_delta, others at -pos_delta
   int pos_delta;         //      (= b; pos_split = b - first anchor row of this launch)
+  int pos_period;        // != 0: anchors span several rank slots (key-side pass of the reduce-scatter
+  int pos_phase;         //      dataflow): view a iff (row + pos_phase) % pos_period < pos_delta
   int nrb;               // row blocks
   int nkt;               // key tiles (128 keys each)
   float c1;              // log2(e) / tau
-  const float* r_row;    // BWD: row factor per anchor row (m_loc floats)
+  const float* r_row;    // BWD: row factor per anchor row (m_loc floats); null = zeros
   const float* r_col;    // BWD: column factor per global key, padded to a multiple of 128 floats
   float* l_out;          // FWD: row sums, m_loc floats, pre-zeroed
   float* dz_acc;         // BWD: m_loc x D fp32, pre-zeroed
@@ -654,12 +656,14 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       const int grow = p.row_global_base + row;                 // same row in key space
       const int g0 = p.row_global_base + rb * C::RB_ROWS + q * 128;
       // key index of this row's positive (masked like the diagonal)
-      const int gpos = row < p.pos_split ? grow + p.pos_delta : grow - p.pos_delta;
+      const bool view_a =
+          p.pos_period ? (row + p.pos_phase) % p.pos_period < p.pos_delta : row < p.pos_split;
+      const int gpos = view_a ? grow + p.pos_delta : grow - p.pos_delta;
       // Key tiles that may hold a diagonal entry or a positive of this Q tile (a Q tile may
       // straddle the view boundary, so both placements) or keys past the end take the
       // per-element predicates: tiles kt_x and kt_x + 1 of each of the three 128-key windows.
       const int kt_d = g0 >> 7, kt_p1 = (g0 - p.pos_delta) >> 7, kt_p2 = (g0 + p.pos_delta) >> 7;
-      cx.r_i = (BWD && valid) ? __ldg(p.r_row + row) : 0.f;
+      cx.r_i = (BWD && valid && p.r_row) ? __ldg(p.r_row + row) : 0.f;
       cx.r_ik = cx.r_i * kscale;
       cx.grow = grow;
       cx.gpos = gpos;

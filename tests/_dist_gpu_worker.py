@@ -29,7 +29,7 @@ def main():
         H1 = torch.randn(world * b, d, generator=g)
         H2 = H1 + 0.5 * torch.randn(world * b, d, generator=g)
         res = {}
-        for kg in (True, False):
+        for kg in (True, False, "reduce_scatter"):
             x = H1[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
             y = H2[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
             loss, _, _ = maai_b200.contrastive_loss(x, y, temperature=tau, local_rank=rank, world_size=world,
@@ -42,8 +42,8 @@ def main():
         if rank == 0:
             h1r = [H1[p * b:(p + 1) * b].numpy() for p in range(world)]
             h2r = [H2[p * b:(p + 1) * b].numpy() for p in range(world)]
-            for kg in (True, False):
-                ol, o1, o2 = O.contrastive_loss_oracle_distributed(h1r, h2r, tau, key_grad=kg)
+            for kg in (True, False, "reduce_scatter"):  # the reduce-scatter dataflow yields the full gradient
+                ol, o1, o2 = O.contrastive_loss_oracle_distributed(h1r, h2r, tau, key_grad=bool(kg))
                 for p in range(world):
                     l = res[kg][p][0]; g1 = res[kg][p][1:1 + b * d].reshape(b, d); g2 = res[kg][p][1 + b * d:].reshape(b, d)
                     e = (abs(l - ol[p]) / abs(ol[p]), np.linalg.norm(g1 - o1[p]) / np.linalg.norm(o1[p]),

@@ -106,6 +106,62 @@ def test_emulated_ranks_fused_topk(world, b, d):
         assert np.mean(np.abs(got - ref[p]) <= 1) > 0.9 and np.abs(got - ref[p]).max() <= max(3, 0.02 * b * world), p
 
 
+@pytest.mark.parametrize("world,b,d,tau", [(2, 96, 128, 0.5), (4, 200, 64, 0.1), (3, 130, 256, 0.2), (8, 64, 128, 0.5)])
+def test_emulated_ranks_reduce_scatter_dataflow(world, b, d, tau):
+    """Key-side reduce-scatter backward: every rank's maai_ntxent_bwd_keyside over
+    its own keys, the reduce_scatter emulated by summing the partial results, then query-side tiles
+    + maai_ntxent_bwd_dh -- must equal the full gradient of the oracle (and of the identity form)."""
+    from maai_b200 import _lib
+    from oracle import ntxent_oracle as O
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(world * 977 + b)
+    H1 = torch.randn(world * b, d, generator=g)
+    H2 = H1 + 0.5 * torch.randn(world * b, d, generator=g)
+    h1r = [H1[p * b:(p + 1) * b].contiguous() for p in range(world)]
+    h2r = [H2[p * b:(p + 1) * b].contiguous() for p in range(world)]
+    dp = lib.maai_padded_dim(d)
+    z_all = torch.zeros(world, 2 * b, dp, dtype=torch.bfloat16, device=dev)
+    inv = torch.zeros(world, 2 * b, device=dev)
+    cos = torch.zeros(world, b, device=dev)
+    dh = [(h1r[p].to(dev), h2r[p].to(dev)) for p in range(world)]
+    for p in range(world):
+        _lib.check(lib.maai_ntxent_normalize(dh[p][0].data_ptr(), dh[p][1].data_ptr(), b, d, 0,
+                                             z_all[p].data_ptr(), inv[p].data_ptr(), cos[p].data_ptr(), s), "k1")
+    rowsum = torch.zeros(world, 2 * b, device=dev)
+    r_loc = torch.zeros(world, 2 * b, device=dev)
+    losses = torch.zeros(world, device=dev)
+    for p in range(world):
+        _lib.check(lib.maai_ntxent_fwd(z_all.data_ptr(), b, world, p, dp, 1.0 / tau, cos[p].data_ptr(),
+                                       rowsum[p].data_ptr(), r_loc[p].data_ptr(), losses[p:].data_ptr(), s), "k2")
+    # every rank's key-side partial sums for ALL anchors, then the reduce-scatter (sum over ranks)
+    total = torch.zeros(world * 2 * b, dp, device=dev)
+    for p in range(world):
+        r_pad = torch.zeros(lib.maai_ntxent_r_len(b, 1), device=dev)
+        r_pad[:2 * b] = r_loc[p]
+        part = torch.full((world * 2 * b, dp), float("nan"), device=dev)  # zeroed inside
+        _lib.check(lib.maai_ntxent_bwd_keyside(z_all.data_ptr(), r_pad.data_ptr(), b, world, p, dp, 1.0 / tau,
+                                               part.data_ptr(), s), "keyside")
+        total += part
+    _, o1f, o2f = O.contrastive_loss_oracle_distributed([h.numpy() for h in h1r], [h.numpy() for h in h2r], tau, key_grad=True)
+    one = torch.ones((), device=dev)
+    zeros = torch.zeros(lib.maai_ntxent_r_len(b, world), device=dev)
+    for p in range(world):
+        acc = torch.empty(2 * b, dp, device=dev)
+        _lib.check(lib.maai_ntxent_bwd_tiles(z_all.data_ptr(), r_loc[p].data_ptr(), zeros.data_ptr(), b, world, p, dp,
+                                             1.0 / tau, 3, acc.data_ptr(), s), "tiles")
+        extra = total[p * 2 * b:(p + 1) * 2 * b].contiguous()
+        g1 = torch.zeros(b, d, device=dev); g2 = torch.zeros(b, d, device=dev)
+        _lib.check(lib.maai_ntxent_bwd_dh(acc.data_ptr(), extra.data_ptr(), rowsum[p].data_ptr(), cos[p].data_ptr(),
+                                          dh[p][0].data_ptr(), dh[p][1].data_ptr(), 0, inv[p].data_ptr(),
+                                          one.data_ptr(), b, d, dp, 1.0 / tau, 1, 3, g1.data_ptr(), g2.data_ptr(), s),
+                   "dh")
+        torch.cuda.synchronize()
+        assert rel_fro(g1.cpu().numpy(), o1f[p]) <= 1e-2, p
+        assert rel_fro(g2.cpu().numpy(), o2f[p]) <= 1e-2, p
+
+
 def test_two_gpu_torchrun(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
