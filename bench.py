@@ -235,6 +235,34 @@ def main():
         return dict(ms_per_step=total_ms / steps, ms_median=statistics.median(ms), launches=launches,
                     spans=spans, loss=float(loss.detach()))
 
+    def timed_graphed(bb, steps, warmup):
+        """same step through maai_b200.GraphedNTXentLoss (forward and backward as one CUDA graph each)"""
+        h1, h2 = make_inputs(bb)
+        x = h1.requires_grad_(True)
+        y = h2.requires_grad_(True)
+        fn = maai_b200.GraphedNTXentLoss(bb, d, tau, dtype=x.dtype, device=dev, hidden1_requires_grad=True)
+
+        def gstep():
+            x.grad = y.grad = None
+            loss = fn(x, y)
+            loss.backward()
+            return loss
+        for _ in range(warmup):
+            gstep()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(steps):
+            flush_buf.fill_(1)
+            a = torch.cuda.Event(enable_timing=True)
+            e = torch.cuda.Event(enable_timing=True)
+            a.record()
+            loss = gstep()
+            e.record()
+            evs.append((a, e))
+        torch.cuda.synchronize()
+        ms = [a.elapsed_time(e) for a, e in evs]
+        return dict(ms_per_step=sum(ms) / steps, loss=float(loss.detach()))
+
     # ---------------- main timed region (device-resident inputs) ----------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -343,6 +371,9 @@ def main():
         secondary = {"workload": workload_name(4096, d, tau), "ms_per_step": s["ms_per_step"],
                      "pairs_per_s": 4096 / (s["ms_per_step"] * 1e-3),
                      "frac_bf16_peak": 24.0 * 4096 ** 2 * d / (s["ms_per_step"] * 1e-3) / (peaks["bf16"] * 1e12)}
+        sg = timed_graphed(4096, max(args.steps, 50), args.warmup)
+        secondary["cuda_graph_ms_per_step"] = sg["ms_per_step"]
+        secondary["cuda_graph_pairs_per_s"] = 4096 / (sg["ms_per_step"] * 1e-3)
 
     # ---------------- secondary: the reference's training call, hidden1 detached ----------------
     # (Contrastive_Learning.py:685-690 passes hidden1=outputs1.data: only dh2 is needed, half of the backward)
@@ -358,8 +389,10 @@ def main():
         from oracle.cpu_baseline import time_port_full
         s0 = timed_run(256, max(args.steps, 100), args.warmup, profile=False)
         c0 = time_port_full(256, d, tau, steps=30, warmup=5)
+        g0 = timed_graphed(256, max(args.steps, 100), args.warmup)
         configs0 = {"workload": workload_name(256, d, tau), "ms_per_step": s0["ms_per_step"],
                     "pairs_per_s": 256 / (s0["ms_per_step"] * 1e-3), "loss": s0["loss"],
+                    "cuda_graph_ms_per_step": g0["ms_per_step"], "cuda_graph_pairs_per_s": 256 / (g0["ms_per_step"] * 1e-3),
                     "cpu_reference_port": {"ms_per_step": c0["s_per_step"] * 1e3, "pairs_per_s": c0["pairs_per_s"],
                                            "cores": c0["threads"], "loss": c0["loss"]},
                     "note": "host-launch-bound on the GPU (9 launches from Python per step); different random "

@@ -514,6 +514,50 @@ def _logits_and_labels(z_all, b, rank, world, temperature):
     return logits_ab, labels
 
 
+class GraphedNTXentLoss(torch.nn.Module):
+    """Single-rank :func:`contrastive_loss` whose forward and backward are each replayed as ONE CUDA
+    graph (``torch.cuda.make_graphed_callables`` around the C-ABI launches, which are all issued on
+    the current stream and allocate nothing outside torch's capturing allocator).
+
+    At the batch sizes the reference trains with (256 - 4096 pairs per GPU, Contrastive_Learning.py:92)
+    a step of this path is a few tens of microseconds of kernels behind ~150 us of Python, ctypes and
+    autograd-engine time; the graph removes the host side.  Shapes, dtype, temperature and which inputs
+    require grad are fixed at construction.  The returned loss is the graph's static output tensor: it
+    is overwritten by the next call (read or clone it before), as with any graphed callable.
+
+        loss_fn = GraphedNTXentLoss(bsz, dim, temperature, hidden1_requires_grad=False, device=dev)
+        loss = loss_fn(outputs1.data, outputs2)        # Contrastive_Learning.py:685-690
+        loss.backward()
+    """
+
+    def __init__(self, bsz, dim, temperature=1.0, dtype=torch.float32, device=None, hidden1_requires_grad=False,
+                 hidden2_requires_grad=True):
+        super().__init__()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if not (hidden1_requires_grad or hidden2_requires_grad):
+            raise ValueError("GraphedNTXentLoss is the training call: at least one input must require grad")
+        t = float(temperature)
+        a = torch.randn(bsz, dim, device=dev).to(dtype).requires_grad_(bool(hidden1_requires_grad))
+        b = torch.randn(bsz, dim, device=dev).to(dtype).requires_grad_(bool(hidden2_requires_grad))
+        _validate(a, b, True, t, 1, 0)
+        _lib.load()
+        self.shape, self.dtype, self.temperature = (int(bsz), int(dim)), dtype, t
+        self.requires = (bool(hidden1_requires_grad), bool(hidden2_requires_grad))
+
+        def fn(h1, h2):
+            return _NTXentFunction.apply(h1, h2, t, 0, 1, None, True, None, False)
+        self._graphed = torch.cuda.make_graphed_callables(fn, (a, b))
+
+    def forward(self, hidden1, hidden2):
+        if tuple(hidden1.shape) != self.shape or tuple(hidden2.shape) != self.shape:
+            raise ValueError(f"GraphedNTXentLoss was captured for shape {self.shape}")
+        if hidden1.dtype != self.dtype or hidden2.dtype != self.dtype:
+            raise TypeError(f"GraphedNTXentLoss was captured for dtype {self.dtype}")
+        if torch.is_grad_enabled() and (hidden1.requires_grad, hidden2.requires_grad) != self.requires:
+            raise ValueError(f"GraphedNTXentLoss was captured for requires_grad = {self.requires}")
+        return self._graphed(hidden1, hidden2)
+
+
 class NTXentLoss(torch.nn.Module):
     """Module form of :func:`contrastive_loss` holding temperature / rank / world / group."""
 

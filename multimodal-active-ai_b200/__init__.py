@@ -5,6 +5,6 @@ the repo root:  ``import maai_b200; maai_b200.contrastive_loss(...)``.
 """
 from . import _lib  # noqa: F401
 from .Model_Util import top_k_accuracy  # noqa: F401
-from .Objective import LARGE_NUM, NTXentLoss, contrastive_loss, padded_dim  # noqa: F401
+from .Objective import LARGE_NUM, GraphedNTXentLoss, NTXentLoss, contrastive_loss, padded_dim  # noqa: F401
 
-__all__ = ["contrastive_loss", "NTXentLoss", "padded_dim", "LARGE_NUM", "top_k_accuracy"]
+__all__ = ["contrastive_loss", "NTXentLoss", "GraphedNTXentLoss", "padded_dim", "LARGE_NUM", "top_k_accuracy"]

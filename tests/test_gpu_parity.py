@@ -336,3 +336,40 @@ def test_symmetric_forward_forced(b, d, tau, aligned):
         assert abs(loss - ol) <= LOSS_TOL * abs(ol), mode
         assert rel_fro(dh1, o1) <= GRAD_TOL and rel_fro(dh2, o2) <= GRAD_TOL, mode
     assert abs(res["1"][0] - res["0"][0]) <= 1e-5 * abs(ol)
+
+
+@pytest.mark.parametrize("b,d,dtype,grad1", [(256, 128, torch.float32, False), (1000, 96, torch.bfloat16, True)])
+def test_graphed_module_matches_eager(b, d, dtype, grad1):
+    """GraphedNTXentLoss (forward / backward replayed as CUDA graphs) == the eager call, on fresh inputs
+    at every replay, and both within the parity bars of the fp64 oracle."""
+    import maai_b200
+    from oracle import ntxent_oracle as O
+    dev = torch.device("cuda:0")
+    tau = 0.2
+    fn = maai_b200.GraphedNTXentLoss(b, d, tau, dtype=dtype, device=dev, hidden1_requires_grad=grad1)
+    g = torch.Generator(device=dev).manual_seed(b + d)
+    for it in range(3):
+        h1 = torch.randn(b, d, generator=g, device=dev).to(dtype)
+        h2 = (h1.float() + 0.5 * torch.randn(b, d, generator=g, device=dev)).to(dtype)
+        res = []
+        for graphed in (True, False):
+            x = h1.clone().requires_grad_(grad1)
+            y = h2.clone().requires_grad_(True)
+            loss = fn(x, y) if graphed else maai_b200.contrastive_loss(x, y, temperature=tau, return_logits=False)[0]
+            loss.backward()
+            res.append((float(loss.detach()), None if x.grad is None else x.grad.float().cpu().numpy(),
+                        y.grad.float().cpu().numpy()))
+        (lg, g1g, g2g), (le, g1e, g2e) = res
+        # same kernels; fp32 atomics across CTAs make the last bits order-dependent
+        assert abs(lg - le) <= 1e-5 * abs(le)
+        assert rel_fro(g2g, g2e) <= (1e-4 if dtype == torch.float32 else 4e-3)
+        if grad1:
+            assert rel_fro(g1g, g1e) <= (1e-4 if dtype == torch.float32 else 4e-3)
+        else:
+            assert g1g is None and g1e is None
+        ol, o1, o2 = O.contrastive_loss_oracle(h1.float().cpu().numpy(), h2.float().cpu().numpy(), tau)
+        assert abs(lg - ol) <= 1e-3 * abs(ol)
+        tol = 1e-2 if dtype == torch.float32 else 2e-2  # bf16 outputs add their own rounding
+        assert rel_fro(g2g, o2) <= tol
+    with pytest.raises(ValueError):
+        fn(torch.zeros(b + 1, d, device=dev, dtype=dtype), torch.zeros(b + 1, d, device=dev, dtype=dtype))
