@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MAAI_ABI_VERSION 4
+#define MAAI_ABI_VERSION 5
 
 #define MAAI_OK 0
 #define MAAI_E_ARG (-1)
@@ -88,6 +88,24 @@ int maai_ntxent_normalize_peer(const void* h1, const void* h2, int b, int d, int
 int maai_ntxent_fwd_peer(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
                          const float* pos_cos, float* rowsum_l, const void* const* peer_r_bases,
                          void* mc_r_base, float* loss_out, void* stream);
+
+/* K2 across ranks with the symmetry of E (world > 1): E_ij = E_ji, so every (anchor slot, key slot)
+ * pair of ranks needs its tiles computed ONCE.  Rank p computes its own block (the tiles on / above the
+ * diagonal) and, for the ranks q = p+1 .. p+world/2 (mod world; the pair at distance world/2 is split
+ * between the two), the tiles (anchors of q) x (keys of p): their column sums are row sums of p's own
+ * anchors (-> rowsum_l), their row sums belong to q's anchors and go to slot q of `stage`.  Half the
+ * MMAs / exp2s of maai_ntxent_fwd.  After a barrier across the ranks, maai_ntxent_fwd_sym_finalize adds
+ * slot `rank` of every other rank's staging vectors (read through peer-mapped addresses) to rowsum_l
+ * (in place), then produces loss and r like maai_ntxent_fwd / maai_ntxent_fwd_peer.
+ *   stage        (world, 2b) fp32, this rank's staging vectors (zeroed inside)
+ *   stage_bases  device array of `world` addresses: every rank's `stage`, as mapped into this process
+ *   r_out        (2b) or NULL;  peer_r_bases / mc_r_base as in maai_ntxent_fwd_peer, or NULL */
+int maai_ntxent_fwd_sym_tiles(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
+                              float* rowsum_l, float* stage, void* stream);
+int maai_ntxent_fwd_sym_finalize(float* rowsum_l, const void* const* stage_bases, int b, int world, int rank,
+                                 float inv_tau, const float* pos_cos, float* r_out,
+                                 const void* const* peer_r_bases, void* mc_r_base, float* loss_out,
+                                 void* stream);
 
 /* K2 for validate() (Contrastive_Learning.py:860-868): the same forward plus, for every view-a anchor
  * k of this rank, pos_rank[k] = number of view-b keys of ALL ranks whose similarity to the anchor is

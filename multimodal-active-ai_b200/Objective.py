@@ -41,7 +41,8 @@ _DTYPES = {torch.float32: _lib.DT_F32, torch.bfloat16: _lib.DT_BF16, torch.float
 class _Profiler:
     """Optional CUDA-event brackets around the C-ABI calls (bench.py's live per-kernel timing)."""
     enabled = False
-    events = {"normalize": [], "gather_z": [], "fwd": [], "gather_r": [], "bwd": []}
+    events = {"normalize": [], "gather_z": [], "fwd": [], "gather_l": [], "finalize": [], "gather_r": [], "bwd": [],
+              "bwd_keyside": [], "reduce_scatter_wait": [], "bwd_dh": []}
 
     @classmethod
     def reset(cls):
@@ -135,7 +136,11 @@ class PeerWorkspace:
         align = lambda x: (x + 255) // 256 * 256
         self.off_z = [i * align(zb) for i in range(self.NBUF)]
         self.off_r = [self.NBUF * align(zb) + i * align(rb) for i in range(self.NBUF)]
-        total = self.NBUF * (align(zb) + align(rb))
+        # staging vectors of the cross-rank symmetric forward: (world, 2b) fp32 partial row sums that
+        # this rank computed for the other ranks' anchors (maai_ntxent_fwd_sym_tiles)
+        sb = world * 2 * b * 4
+        self.off_s = [self.NBUF * (align(zb) + align(rb)) + i * align(sb) for i in range(self.NBUF)]
+        total = self.NBUF * (align(zb) + align(rb) + align(sb))
         self.raw = symm_mem.empty((total,), dtype=torch.uint8, device=device)
         self.raw.zero_()                                 # r padding must read as zero
         self.hdl = symm_mem.rendezvous(self.raw, group if group is not None else dist.group.WORLD)
@@ -143,6 +148,8 @@ class PeerWorkspace:
         tab = lambda off: torch.tensor([p + off for p in ptrs], dtype=torch.int64, device=device)
         self.z_tab = [tab(o) for o in self.off_z]        # device arrays of peer base addresses
         self.r_tab = [tab(o) for o in self.off_r]
+        self.s_tab = [tab(o) for o in self.off_s]
+        self.stage = [self.raw[o:o + sb].view(torch.float32) for o in self.off_s]
         self.z = [self.raw[o:o + zb].view(torch.bfloat16).view(world, 2 * b, dp) for o in self.off_z]
         self.r = [self.raw[o:o + rb].view(torch.float32) for o in self.off_r]
         # NVSwitch multicast mapping of the same allocation (one store reaches every rank), if the
@@ -181,6 +188,17 @@ class PeerWorkspace:
 
 
 _peer_state = {"ok": None}
+
+
+def _sym_forward_enabled(b, dp, world) -> bool:
+    """Cross-rank symmetric forward (peer mode only): on unless MAAI_FWD_SYM_MULTI=0; same size rule
+    as the single-rank symmetric forward for d_pad = 256; at most 16 ranks (group table of the kernel)."""
+    v = os.environ.get("MAAI_FWD_SYM_MULTI", "")
+    if v == "0" or world > 16:
+        return False
+    if v == "1":
+        return True
+    return dp <= 128 or 2 * b >= 16384
 
 
 def peer_gather_available() -> bool:
@@ -311,18 +329,35 @@ class _NTXentFunction(torch.autograd.Function):
         with _Profiler.span("gather_z"):
             ws.hdl.barrier(channel=0)  # every rank's rows have landed in every buffer
         r_row = r_col = None
-        with _Profiler.span("fwd"):
-            if needs_grad and full:
-                _lib.check(lib.maai_ntxent_fwd_peer(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(pos_cos),
-                                                    _ptr(rowsum), _ptr(ws.r_tab[i]), ws.mc_r[i], _ptr(loss),
-                                                    _stream()),
-                           "maai_ntxent_fwd_peer")
-            else:
-                if needs_grad:  # keys detached (reference semantics): local row factors only, r_col = 0
-                    r_row = torch.empty(2 * b, dtype=torch.float32, device=dev)
-                    r_col = torch.zeros(ws.r_len, dtype=torch.float32, device=dev)
-                _lib.check(lib.maai_ntxent_fwd(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(pos_cos),
-                                               _ptr(rowsum), _ptr(r_row), _ptr(loss), _stream()), "maai_ntxent_fwd")
+        peer_r = needs_grad and full
+        if not peer_r and needs_grad:  # keys detached (reference semantics): local row factors only, r_col = 0
+            r_row = torch.empty(2 * b, dtype=torch.float32, device=dev)
+            r_col = torch.zeros(ws.r_len, dtype=torch.float32, device=dev)
+        if _sym_forward_enabled(b, dp, world):
+            # every pair of rank slots is computed once: own block + the anchors of the ranks ahead on
+            # the ring against the local keys; the other half of each row sum arrives through the
+            # peers' staging vectors after a barrier
+            with _Profiler.span("fwd"):
+                _lib.check(lib.maai_ntxent_fwd_sym_tiles(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(rowsum),
+                                                         _ptr(ws.stage[i]), _stream()), "maai_ntxent_fwd_sym_tiles")
+            with _Profiler.span("gather_l"):
+                ws.hdl.barrier(channel=2)
+            with _Profiler.span("finalize"):
+                _lib.check(lib.maai_ntxent_fwd_sym_finalize(_ptr(rowsum), _ptr(ws.s_tab[i]), b, world, rank, inv_tau,
+                                                            _ptr(pos_cos), _ptr(r_row),
+                                                            _ptr(ws.r_tab[i]) if peer_r else None,
+                                                            ws.mc_r[i] if peer_r else None, _ptr(loss), _stream()),
+                           "maai_ntxent_fwd_sym_finalize")
+        else:
+            with _Profiler.span("fwd"):
+                if peer_r:
+                    _lib.check(lib.maai_ntxent_fwd_peer(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(pos_cos),
+                                                        _ptr(rowsum), _ptr(ws.r_tab[i]), ws.mc_r[i], _ptr(loss),
+                                                        _stream()),
+                               "maai_ntxent_fwd_peer")
+                else:
+                    _lib.check(lib.maai_ntxent_fwd(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(pos_cos),
+                                                   _ptr(rowsum), _ptr(r_row), _ptr(loss), _stream()), "maai_ntxent_fwd")
         if needs_grad:
             if full:
                 with _Profiler.span("gather_r"):

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # MAAI_DEBUG_LIB selects an A/B build of the same library (tools/ab_variants.py); never a fallback
 LIB_PATH = os.environ.get("MAAI_DEBUG_LIB") or os.path.join(HERE, "libmaai_ntxent.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 OK, E_ARG, E_SHAPE, E_CUDA = 0, -1, -2, -3
 DT_F32, DT_BF16, DT_F16 = 0, 1, 2
 
@@ -34,6 +34,10 @@ SIGNATURES = {
     "maai_ntxent_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                  _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
                                  _c_float, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+    "maai_ntxent_fwd_sym_tiles": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p,
+                                           _c_void_p]),
+    "maai_ntxent_fwd_sym_finalize": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p,
+                                              _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "maai_ntxent_bwd_tiles": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float,
                                        _c_int, _c_void_p, _c_void_p]),
     "maai_ntxent_bwd_keyside": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float,

@@ -318,11 +318,77 @@ static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, f
                               nullptr, rowsum_l, nullptr, b, b, s);
   }
   if (rc != MAAI_OK) return rc;
-  MAAI_CUDA(launch_k(maai::finalize_loss_kernel, dim3(maai::kFinalizeCluster), dim3(1024), 0, s,
-                     static_cast<const float*>(rowsum_l), pos_cos, b, inv_tau, r_out, loss_out,
-                     reinterpret_cast<const unsigned long long*>(peer_r), world, rank, static_cast<float*>(mc_r)));
+  MAAI_CUDA(launch_k(maai::finalize_loss_kernel, dim3(maai::kFinalizeCluster), dim3(1024), 0, s, rowsum_l,
+                     pos_cos, b, inv_tau, r_out, loss_out, reinterpret_cast<const unsigned long long*>(peer_r),
+                     world, rank, static_cast<float*>(mc_r), static_cast<const unsigned long long*>(nullptr)));
   return MAAI_OK;
 }
+
+// Symmetric forward across ranks, tile part: this rank's own block (triangular) + the anchor groups
+// of the ranks "ahead" of it on the ring against its own keys (see maai_ntxent.h).
+extern "C++" {
+template <int D, int NQ>
+static int launch_tile_groups(const void* z_glob, int b, int world, int rank, float inv_tau, float* rowsum_l,
+                              float* stage, cudaStream_t s) {
+  using C = maai::TileCfg<D, false, NQ>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(maai::ntxent_tile_kernel<D, false, NQ, false, true, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(smem)", attr_err);
+  const int m_loc = 2 * b, m_glob = 2 * b * world;
+  const char* k_base = static_cast<const char*>(z_glob) + (size_t)rank * m_loc * D * 2;
+  CUtensorMap tq, tk;
+  int rc;
+  if ((rc = make_rows_tmap(&tq, z_glob, m_glob, D)) != MAAI_OK) return rc;
+  if ((rc = make_rows_tmap(&tk, k_base, m_loc, D)) != MAAI_OK) return rc;
+  maai::TileParams p{};
+  p.m_loc = m_loc;
+  p.m_glob = m_loc;  // key space = this rank's slot
+  p.row_global_base = 0;
+  p.pos_split = b;
+  p.pos_delta = b;
+  p.nrb = (m_loc + C::RB_ROWS - 1) / C::RB_ROWS;
+  p.nkt = (m_loc + C::KT - 1) / C::KT;
+  p.c1 = inv_tau * 1.4426950408889634f;
+  p.l_out = rowsum_l;
+  p.pv_lbo = C::CHUNK_BYTES;
+  p.pv_sbo = 1024;
+  const int T = p.nkt, Th = (T + 1) / 2;
+  int ng = 0;
+  long long total = (long long)p.nrb * T - (long long)NQ * p.nrb * (p.nrb - 1) / 2;
+  auto add = [&](int qrow0, int rows, int nkt, float* out) {
+    p.g_qrow0[ng] = qrow0;
+    p.g_rows[ng] = rows;
+    p.g_nkt[ng] = nkt;
+    p.g_out[ng] = out;
+    if (ng > 0) total += (long long)((rows + C::RB_ROWS - 1) / C::RB_ROWS) * nkt;
+    ++ng;
+  };
+  add(rank * m_loc, m_loc, T, rowsum_l);
+  for (int dist = 1; 2 * dist <= world; ++dist) {
+    const int q = (rank + dist) % world;  // owner of the anchors
+    float* out = stage + (size_t)q * m_loc;
+    if (2 * dist < world) {
+      add(q * m_loc, m_loc, T, out);
+    } else if (rank < q) {  // the pair at distance world/2 is split: lower rank takes its first key tiles
+      add(q * m_loc, m_loc, Th, out);
+    } else if (m_loc - Th * 128 > 0) {  // higher rank: the lower rank's anchors that are not among those keys
+      add(q * m_loc + Th * 128, m_loc - Th * 128, T, out + Th * 128);
+    }
+  }
+  p.ngroups = ng;
+  p.total_items = total;
+  int sms = sm_count();
+  if (sms <= 0) return fail(MAAI_E_CUDA, "no CUDA device");
+  const int grid = (int)(total < sms ? total : sms);
+  MAAI_CUDA(launch_k(maai::ntxent_tile_kernel<D, false, NQ, false, true, true>, dim3(grid), dim3(C::NTHREADS),
+                     C::SMEM_BYTES, s, tq, tk, p));
+  return MAAI_OK;
+}
+}  // extern "C++"
 
 int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
                     const float* pos_cos, float* rowsum_l, float* r_out, float* loss_out,
@@ -372,6 +438,41 @@ int maai_ntxent_fwd_peer(const void* z_glob, int b, int world, int rank, int d_p
   if (!peer_r_bases) return fail(MAAI_E_ARG, "null pointer");
   return fwd_impl(z_glob, b, world, rank, d_pad, inv_tau, pos_cos, rowsum_l, nullptr, loss_out, nullptr,
                   stream, peer_r_bases, mc_r_base);
+}
+
+int maai_ntxent_fwd_sym_tiles(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
+                              float* rowsum_l, float* stage, void* stream) {
+  if (!z_glob || !rowsum_l || !stage) return fail(MAAI_E_ARG, "null pointer");
+  int rc = check_common(b, world, rank);
+  if (rc != MAAI_OK) return rc;
+  if (world > 2 * (maai::kMaxGroups - 1)) return fail(MAAI_E_SHAPE, "symmetric forward: world must be <= 16");
+  if (!(inv_tau > 0.f)) return fail(MAAI_E_ARG, "temperature must be positive");
+  if (!aligned16(z_glob)) return fail(MAAI_E_ARG, "z_glob must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if ((rc = zero_words(rowsum_l, (size_t)2 * b, s)) != MAAI_OK) return rc;
+  if ((rc = zero_words(stage, (size_t)2 * b * world, s)) != MAAI_OK) return rc;
+  switch (d_pad) {
+    case 64: return launch_tile_groups<64, 2>(z_glob, b, world, rank, inv_tau, rowsum_l, stage, s);
+    case 128: return launch_tile_groups<128, 2>(z_glob, b, world, rank, inv_tau, rowsum_l, stage, s);
+    case 256: return launch_tile_groups<256, 1>(z_glob, b, world, rank, inv_tau, rowsum_l, stage, s);
+    default: return fail(MAAI_E_SHAPE, "d_pad must be 64, 128 or 256");
+  }
+}
+
+int maai_ntxent_fwd_sym_finalize(float* rowsum_l, const void* const* stage_bases, int b, int world, int rank,
+                                 float inv_tau, const float* pos_cos, float* r_out,
+                                 const void* const* peer_r_bases, void* mc_r_base, float* loss_out,
+                                 void* stream) {
+  if (!rowsum_l || !stage_bases || !pos_cos || !loss_out) return fail(MAAI_E_ARG, "null pointer");
+  int rc = check_common(b, world, rank);
+  if (rc != MAAI_OK) return rc;
+  if (!(inv_tau > 0.f)) return fail(MAAI_E_ARG, "temperature must be positive");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MAAI_CUDA(launch_k(maai::finalize_loss_kernel, dim3(maai::kFinalizeCluster), dim3(1024), 0, s, rowsum_l,
+                     pos_cos, b, inv_tau, r_out, loss_out,
+                     reinterpret_cast<const unsigned long long*>(peer_r_bases), world, rank,
+                     static_cast<float*>(mc_r_base), reinterpret_cast<const unsigned long long*>(stage_bases)));
+  return MAAI_OK;
 }
 
 int maai_ntxent_fwd_eval(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,

@@ -163,13 +163,14 @@ normalize_cast_peer_kernel(const T* __restrict__ h1, const T* __restrict__ h2, i
 //   lse_i - s_i,pos = ln(e_pos + l'_i) - ln(e_pos) = log1p(l'_i / e_pos)      (Objective.py:76-77)
 //   loss = (1/b) * sum_{i < 2b} log1p(l'_i / e_pos(i))                          (Objective.py:79)
 // and r_i = 1 / (b * (e_pos + l'_i)) for the backward.  r_out may be null.  peer_r (optional): device
-// array of `world` peer-mapped base addresses of every rank's gathered r array.
+// array of `world` peer-mapped base addresses of every rank's gathered r array.  stage_tab (optional):
+// `world` peer-mapped base addresses of every rank's (world, 2b) staging vectors (maai_ntxent_fwd_sym).
 constexpr int kFinalizeCluster = 8;
 __global__ void __cluster_dims__(kFinalizeCluster, 1, 1) __launch_bounds__(1024)
-finalize_loss_kernel(const float* __restrict__ l, const float* __restrict__ pos_cos, int b,
+finalize_loss_kernel(float* __restrict__ l, const float* __restrict__ pos_cos, int b,
                      float inv_tau, float* __restrict__ r_out, float* __restrict__ loss_out,
                      const unsigned long long* __restrict__ peer_r = nullptr, int world = 1, int my_rank = 0,
-                     float* mc_r = nullptr) {
+                     float* mc_r = nullptr, const unsigned long long* __restrict__ stage_tab = nullptr) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ double part[32];
@@ -181,7 +182,15 @@ finalize_loss_kernel(const float* __restrict__ l, const float* __restrict__ pos_
   const float inv_b = 1.f / float(b);
   const float c1 = inv_tau * 1.4426950408889634f;
   for (int i = rank * blockDim.x + threadIdx.x; i < 2 * b; i += kFinalizeCluster * blockDim.x) {
-    const float ln = l[i];
+    float ln = l[i];
+    if (stage_tab) {
+      // symmetric forward across ranks: the other ranks hold partial row sums of this rank's anchors
+      // (the tiles they computed for their own column sums) in slot my_rank of their staging vectors;
+      // read them over NVLink (uncached: written by the peers' kernels before the barrier)
+      for (int p = 0; p < world; ++p)
+        if (p != my_rank) ln += __ldcv(reinterpret_cast<const float*>(stage_tab[p]) + (size_t)my_rank * 2 * b + i);
+      l[i] = ln;  // the backward's positive-pair term needs the complete row sum
+    }
     const float ep = ex2_approx(fmaf(pos_cos[i < b ? i : i - b], c1, -c1));
     acc += double(log1pf(ln / ep));
     const float r = inv_b / (ep + ln);

@@ -38,6 +38,8 @@
 //   one-buffer-per-Q-tile layout).  All 16 softmax warps work on every S tile (32 columns per
 //   thread), which halves the latency of the softmax stage of each tile.
 #pragma once
+#include <type_traits>
+
 #include "ptx_sm100.cuh"
 
 // Of every 8 column pairs a softmax thread handles, this many take the polynomial exp2 on the FMA
@@ -129,6 +131,8 @@ __device__ long long g_prof[160 * 20 * 8];
 #define PROF_FLUSH() do { } while (0)
 #endif
 
+constexpr int kMaxGroups = 9;  // own block + up to 8 remote anchor groups (world <= 16)
+
 struct TileParams {
   int m_loc;             // anchor rows covered by tmap_q
   int m_glob;            // key rows covered by tmap_k
@@ -150,6 +154,16 @@ struct TileParams {
   // similar than its positive (contrastive top-k without logits, Model_Util.py:104-113)
   const float* pos_cos;  // positive cosine per local pair (pos_split floats)
   int* rank_out;         // pos_split ints, pre-zeroed
+  // GRP (symmetric forward across ranks, keys = this rank's slot): group 0 = this rank's own anchors
+  // (triangular, as SYM); groups 1.. = anchors of another rank's slot (rows of tmap_q from g_qrow0)
+  // against this rank's key tiles [0, g_nkt): every tile adds its row sums to the group's g_out
+  // (a staging vector the owner of those anchors collects later) and its column sums to l_out.
+  long long total_items;
+  int ngroups;
+  int g_qrow0[kMaxGroups];
+  int g_rows[kMaxGroups];
+  int g_nkt[kMaxGroups];
+  float* g_out[kMaxGroups];
 };
 
 template <int D, bool BWD, int NQ>
@@ -314,7 +328,8 @@ struct SegWalk {
   int nkt;
   int rb = 0;
   long long cum = 0;  // items before row block rb
-  __device__ __forceinline__ explicit SegWalk(int nkt_) : nkt(nkt_) {}
+  static constexpr int g = 0;
+  __device__ __forceinline__ explicit SegWalk(const TileParams& p) : nkt(p.nkt) {}
   __device__ __forceinline__ int cnt(int r) const { return SYM ? nkt - NQ * r : nkt; }
   // segment that starts at item `it`: row block, first key tile, number of key tiles
   __device__ __forceinline__ void locate(long long it, long long it_end, int& rb_out, int& j0, int& n) {
@@ -335,10 +350,34 @@ struct SegWalk {
   }
 };
 
-template <int D, bool BWD, int NQ, bool RANK = false, bool SYM = false>
+// GRP: the item list is group after group; group 0 triangular (like SYM), the others rectangular.
+template <int NQ>
+struct GrpWalk {
+  const TileParams& p;
+  int g = 0;
+  int rb = 0;         // row block inside group g
+  long long cum = 0;  // items before (g, rb)
+  __device__ __forceinline__ explicit GrpWalk(const TileParams& p_) : p(p_) {}
+  __device__ __forceinline__ int cnt() const { return g == 0 ? p.g_nkt[0] - NQ * rb : p.g_nkt[g]; }
+  __device__ __forceinline__ void locate(long long it, long long it_end, int& rb_out, int& j0, int& n) {
+    while (it >= cum + cnt()) {
+      cum += cnt();
+      if (++rb * (128 * NQ) >= p.g_rows[g]) {
+        rb = 0;
+        ++g;
+      }
+    }
+    const int off = int(it - cum);
+    rb_out = rb;
+    j0 = (g == 0 ? NQ * rb : 0) + off;
+    n = int(min((long long)(cnt() - off), it_end - it));
+  }
+};
+
+template <int D, bool BWD, int NQ, bool RANK = false, bool SYM = false, bool GRP = false>
 __global__ void __launch_bounds__(640, 1)
 ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
-                   const __grid_constant__ CUtensorMap tmap_k, const TileParams p) {
+                   const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ TileParams p) {
   using C = TileCfg<D, BWD, NQ>;
   constexpr int NST = C::NST, NB = C::NB;
 
@@ -369,9 +408,12 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
   // ---- this CTA's contiguous range of (row block, key tile) items ----
   static_assert(!SYM || (!BWD && !RANK && MAAI_FWD_CW == 32 && (NQ == 2 || MAAI_NQ1_TEAMS == 2)),
                 "symmetric mode: plain forward, 64 columns per softmax thread in 32-column chunks");
+  static_assert(!GRP || SYM, "anchor groups are a variant of the symmetric forward");
+  using Walk = typename std::conditional<GRP, GrpWalk<NQ>, SegWalk<SYM, NQ>>::type;
   // sum over rb of (nkt - NQ rb)
-  const long long total = SYM ? (long long)p.nrb * p.nkt - (long long)NQ * p.nrb * (p.nrb - 1) / 2
-                              : (long long)p.nrb * p.nkt;
+  const long long total = GRP ? p.total_items
+                          : SYM ? (long long)p.nrb * p.nkt - (long long)NQ * p.nrb * (p.nrb - 1) / 2
+                                : (long long)p.nrb * p.nkt;
   const long long it_begin = total * blockIdx.x / gridDim.x;
   const long long it_end = total * (blockIdx.x + 1) / gridDim.x;
 
@@ -412,7 +454,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
     if (lane == 0) {
       PROF_INIT();
       uint32_t t = 0, useg = 0;
-      SegWalk<SYM, NQ> walk(p.nkt);
+      Walk walk(p);
       for (long long it = it_begin; it < it_end;) {
         int rb, j0, n;
         walk.locate(it, it_end, rb, j0, n);
@@ -424,7 +466,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll
           for (int c = 0; c < C::CHUNKS; ++c)
             tma_load_2d(sQ + q * C::TILE_BYTES + c * C::CHUNK_BYTES, &tmap_q, c * 64,
-                        rb * C::RB_ROWS + q * 128, bar_q_full);
+                        (GRP ? p.g_qrow0[walk.g] : 0) + rb * C::RB_ROWS + q * 128, bar_q_full);
         for (int jj = 0; jj < n; ++jj, ++t) {
           const int st = t % NST;
           mbar_wait(bar_k_empty(st), ((t / NST) & 1) ^ 1);
@@ -520,7 +562,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       PROF_MARK(3);
     };
 
-    SegWalk<SYM, NQ> walk(p.nkt);
+    Walk walk(p);
     uint32_t symu[2] = {0, 0};  // SYM: S tiles issued so far per team (a team skips tiles below the diagonal)
 #pragma unroll 1
     for (long long it = it_begin; it < it_end;) {
@@ -553,7 +595,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
           PROF_MARK(0);
           // Q tile 1 of the row block sits one key tile further down the diagonal: its tile with the
           // first key tile of the block (kt == 2 rb) lies below the diagonal and is not computed
-          const int nq_here = (j0 + jj < 2 * rb + 1) ? 1 : 2;
+          const int nq_here = (!(GRP && walk.g > 0) && j0 + jj < 2 * rb + 1) ? 1 : 2;
           for (int q = 0; q < nq_here; ++q) {
             issue_s(symu[q] * 2 + q, q, st);
             ++symu[q];
@@ -642,7 +684,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
     for (int i = 0; i < 8; ++i) cx.prof_a[i] = 0;
 #endif
 
-    SegWalk<SYM, NQ> walk(p.nkt);
+    Walk walk(p);
     // SYM: partial row sums of the tiles above the diagonal, in the 16x256b fragment layout: slot k of
     // a thread is tile row 32 w4 + 8 k + lane / 4 (k = 0..3), summed over the thread's columns
     float2 racc_m[4], racc_p[4];
@@ -651,8 +693,11 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       int rb, j0, n;
       walk.locate(it, it_end, rb, j0, n);
       const int q = (NQ == 2) ? team : 0;
-      const int row = rb * C::RB_ROWS + q * 128 + row_in_tile;  // anchor row (local)
-      const bool valid = row < p.m_loc;
+      const int grp = GRP ? walk.g : 0;
+      const bool remote = GRP && grp > 0;                       // anchors of another rank's slot
+      const int rows_here = GRP ? p.g_rows[grp] : p.m_loc;
+      const int row = rb * C::RB_ROWS + q * 128 + row_in_tile;  // anchor row (local / inside the group)
+      const bool valid = row < rows_here;
       const int grow = p.row_global_base + row;                 // same row in key space
       const int g0 = p.row_global_base + rb * C::RB_ROWS + q * 128;
       // key index of this row's positive (masked like the diagonal)
@@ -663,6 +708,9 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       // straddle the view boundary, so both placements) or keys past the end take the
       // per-element predicates: tiles kt_x and kt_x + 1 of each of the three 128-key windows.
       const int kt_d = g0 >> 7, kt_p1 = (g0 - p.pos_delta) >> 7, kt_p2 = (g0 + p.pos_delta) >> 7;
+      // remote anchors meet neither themselves nor their positives among the local keys; only rows
+      // past the end of the group (they belong to the next slot) have to be kept out of the column sums
+      const bool ragged_rows = GRP && rb * C::RB_ROWS + q * 128 + 128 > rows_here;
       cx.r_i = (BWD && valid && p.r_row) ? __ldg(p.r_row + row) : 0.f;
       cx.r_ik = cx.r_i * kscale;
       cx.grow = grow;
@@ -686,11 +734,12 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
         const int kt = j0 + jj;
         // SYM: key tile kt against row tile 2 rb + q: below the diagonal -> not computed at all,
         // on it -> ordinary tile (row sums), above it -> row sums AND column sums
-        if (SYM && kt < NQ * rb + q) continue;
-        const bool upper = SYM && kt > NQ * rb + q;
+        if (SYM && !remote && kt < NQ * rb + q) continue;
+        const bool upper = SYM && (remote || kt > NQ * rb + q);
         const int buf = (NQ == 2) ? team * MODB + sb : sb;
-        const bool special = unsigned(kt - kt_d) <= 1u || unsigned(kt - kt_p1) <= 1u ||
-                             unsigned(kt - kt_p2) <= 1u || kt == kt_ragged;
+        const bool special = remote ? (ragged_rows || kt == kt_ragged)
+                                    : (unsigned(kt - kt_d) <= 1u || unsigned(kt - kt_p1) <= 1u ||
+                                       unsigned(kt - kt_p2) <= 1u || kt == kt_ragged || ragged_rows);
         int cmode = 0;
         if (RANK) {  // which keys of this tile are view-b keys: none / all / mixed
           const int seg_lo = (kt * C::KT) / p.pos_delta, seg_hi = (kt * C::KT + C::KT - 1) / p.pos_delta;
@@ -762,11 +811,12 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #pragma unroll
                 for (int hi = 0; hi < 2; ++hi) {
                   const int lr = rb * C::RB_ROWS + q * 128 + r_lo + 8 * (2 * h + hi);
-                  const int gr = p.row_global_base + lr;
-                  const int gp = lr < p.pos_split ? gr + p.pos_delta : gr - p.pos_delta;
+                  const int gr = remote ? -1 : p.row_global_base + lr;
+                  const int gp = remote ? -1 : (lr < p.pos_split ? gr + p.pos_delta : gr - p.pos_delta);
                   const int kc = kt * C::KT + col_off + c * 32 + 8 * g + c_lo;
-                  if (kc == gp || kc == gr || kc >= p.m_glob) e[2 * g + hi].x = 0.f;
-                  if (kc + 1 == gp || kc + 1 == gr || kc + 1 >= p.m_glob) e[2 * g + hi].y = 0.f;
+                  const bool rbad = GRP && lr >= rows_here;
+                  if (rbad || kc == gp || kc == gr || kc >= p.m_glob) e[2 * g + hi].x = 0.f;
+                  if (rbad || kc + 1 == gp || kc + 1 == gr || kc + 1 >= p.m_glob) e[2 * g + hi].y = 0.f;
                 }
               }
             }
@@ -913,7 +963,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       }
 
       if (!BWD) {
-        if (valid) {
+        if (valid && !remote) {
           const float2 sm = __fadd2_rn(acc_m[0], acc_m[1]), sp = __fadd2_rn(acc_p[0], acc_p[1]);
           atomicAdd(p.l_out + row, (sm.x + sm.y) + kscale * (sp.x + sp.y));
           if (RANK && row < p.pos_split && cx.cnt) atomicAdd(p.rank_out + row, cx.cnt);
@@ -925,7 +975,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
             v += __shfl_xor_sync(0xffffffffu, v, 1);
             v += __shfl_xor_sync(0xffffffffu, v, 2);
             const int lr = rb * C::RB_ROWS + q * 128 + w4 * 32 + 8 * k + (lane >> 2);
-            if ((lane & 3) == 0 && lr < p.m_loc) atomicAdd(p.l_out + lr, v);
+            if ((lane & 3) == 0 && lr < rows_here) atomicAdd((GRP ? p.g_out[grp] : p.l_out) + lr, v);
           }
         }
       } else {

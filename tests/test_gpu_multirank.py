@@ -162,6 +162,62 @@ def test_emulated_ranks_reduce_scatter_dataflow(world, b, d, tau):
         assert rel_fro(g2.cpu().numpy(), o2f[p]) <= 1e-2, p
 
 
+@pytest.mark.parametrize("world,b,d,tau", [(2, 96, 128, 0.5), (2, 700, 128, 0.2), (4, 200, 64, 0.1), (3, 130, 256, 0.2),
+                                           (8, 64, 128, 0.5), (8, 333, 96, 0.5), (5, 1024, 128, 0.3), (16, 40, 32, 0.5)])
+def test_emulated_ranks_symmetric_forward(world, b, d, tau):
+    """Cross-rank symmetric forward (maai_ntxent_fwd_sym_tiles + barrier + maai_ntxent_fwd_sym_finalize):
+    every pair of rank slots is computed once; row sums, row factors and losses must equal those of the
+    full forward (maai_ntxent_fwd) and the fp64 oracle.  Ranks are run one after the other on one GPU,
+    the 'peer' addresses are the ranks' own staging buffers."""
+    from maai_b200 import _lib
+    from oracle import ntxent_oracle as O
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(world * 31 + b)
+    H1 = torch.randn(world * b, d, generator=g)
+    H2 = H1 + 0.5 * torch.randn(world * b, d, generator=g)
+    h1r = [H1[p * b:(p + 1) * b].contiguous() for p in range(world)]
+    h2r = [H2[p * b:(p + 1) * b].contiguous() for p in range(world)]
+    dp = lib.maai_padded_dim(d)
+    z_all = torch.zeros(world, 2 * b, dp, dtype=torch.bfloat16, device=dev)
+    inv = torch.zeros(world, 2 * b, device=dev)
+    cos = torch.zeros(world, b, device=dev)
+    for p in range(world):
+        a, c = h1r[p].to(dev), h2r[p].to(dev)
+        _lib.check(lib.maai_ntxent_normalize(a.data_ptr(), c.data_ptr(), b, d, 0, z_all[p].data_ptr(),
+                                             inv[p].data_ptr(), cos[p].data_ptr(), s), "k1")
+    # reference: the full forward of every rank
+    rowsum_full = torch.zeros(world, 2 * b, device=dev)
+    r_full = torch.zeros(world, 2 * b, device=dev)
+    loss_full = torch.zeros(world, device=dev)
+    for p in range(world):
+        _lib.check(lib.maai_ntxent_fwd(z_all.data_ptr(), b, world, p, dp, 1.0 / tau, cos[p].data_ptr(),
+                                       rowsum_full[p].data_ptr(), r_full[p].data_ptr(), loss_full[p:].data_ptr(), s), "k2")
+    # symmetric: tile part of every rank, "barrier", then the finalize of every rank
+    rowsum = torch.full((world, 2 * b), float("nan"), device=dev)
+    stage = torch.full((world, world, 2 * b), float("nan"), device=dev)  # stage[p] = rank p's staging vectors
+    for p in range(world):
+        _lib.check(lib.maai_ntxent_fwd_sym_tiles(z_all.data_ptr(), b, world, p, dp, 1.0 / tau, rowsum[p].data_ptr(),
+                                                 stage[p].data_ptr(), s), "sym tiles")
+    torch.cuda.synchronize()
+    tab = torch.tensor([stage[p].data_ptr() for p in range(world)], dtype=torch.int64, device=dev)
+    r_sym = torch.zeros(world, 2 * b, device=dev)
+    loss_sym = torch.zeros(world, device=dev)
+    for p in range(world):
+        _lib.check(lib.maai_ntxent_fwd_sym_finalize(rowsum[p].data_ptr(), tab.data_ptr(), b, world, p, 1.0 / tau,
+                                                    cos[p].data_ptr(), r_sym[p].data_ptr(), None, None,
+                                                    loss_sym[p:].data_ptr(), s), "sym finalize")
+    torch.cuda.synchronize()
+    # (polynomial / MUFU exp2 assignment differs between the two tile walks: agreement to ~1e-4, not bitwise)
+    assert torch.allclose(rowsum, rowsum_full, rtol=2e-3, atol=1e-6), (rowsum - rowsum_full).abs().max()
+    assert torch.allclose(r_sym, r_full, rtol=2e-3, atol=0)
+    ol, _, _ = O.contrastive_loss_oracle_distributed([h.numpy() for h in h1r], [h.numpy() for h in h2r], tau, key_grad=False)
+    got = loss_sym.cpu().numpy()
+    for p in range(world):
+        assert abs(got[p] - ol[p]) <= 1e-3 * abs(ol[p]), (p, got[p], ol[p])
+
+
 def test_two_gpu_torchrun(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
