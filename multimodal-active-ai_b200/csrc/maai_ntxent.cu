@@ -364,7 +364,8 @@ static int launch_tile_groups(const void* z_glob, int b, int world, int rank, fl
     p.g_rows[ng] = rows;
     p.g_nkt[ng] = nkt;
     p.g_out[ng] = out;
-    if (ng > 0) total += (long long)((rows + C::RB_ROWS - 1) / C::RB_ROWS) * nkt;
+    p.g_items[ng] = ng == 0 ? total : (long long)((rows + C::RB_ROWS - 1) / C::RB_ROWS) * nkt;
+    if (ng > 0) total += p.g_items[ng];
     ++ng;
   };
   add(rank * m_loc, m_loc, T, rowsum_l);

@@ -163,6 +163,7 @@ struct TileParams {
   int g_qrow0[kMaxGroups];
   int g_rows[kMaxGroups];
   int g_nkt[kMaxGroups];
+  long long g_items[kMaxGroups];  // items of the group (row blocks x key tiles; group 0 triangular)
   float* g_out[kMaxGroups];
 };
 
@@ -319,29 +320,44 @@ __device__ __forceinline__ void softmax_chunk(uint32_t (&v)[CW], uint32_t (&pk)[
   CX_MARK(2);
 }
 
+// Triangular item list (row block r holds T - NQ r key tiles), FOLDED: the row blocks are visited in
+// the order 0, nrb-1, 1, nrb-2, ... so that every pair of consecutive segments holds the same
+// S = 2T - NQ (nrb - 1) items.  A CTA's contiguous range of N items then spans about 2N/S segments
+// wherever it lies; in row-block order the last CTA collected all the short segments (21 of them at
+// 32768 pairs: each segment costs a Q-tile load + a pipeline refill, ~3-5 us).
+template <int NQ>
+__device__ __forceinline__ void tri_locate(long long idx, int T, int nrb, int& rb, int& off, int& cnt) {
+  const int S = 2 * T - NQ * (nrb - 1);
+  const int pr = int(idx / S);
+  const int r = int(idx - (long long)pr * S);
+  const int a = T - NQ * pr;
+  if (r < a) {
+    rb = pr;
+    off = r;
+    cnt = a;
+  } else {
+    rb = nrb - 1 - pr;
+    off = r - a;
+    cnt = T - NQ * rb;
+  }
+}
+
 // Walks the CTA's item range segment by segment (a segment = a maximal run of key tiles inside one
 // row block).  SYM (symmetric forward, anchors == keys): row block rb only visits key tiles
 // kt >= 2*rb, because E_ij = E_ji lets every tile above the diagonal contribute its row sums to the
 // anchors AND its column sums to the keys; the tiles below the diagonal are never computed.
 template <bool SYM, int NQ>
 struct SegWalk {
-  int nkt;
-  int rb = 0;
-  long long cum = 0;  // items before row block rb
+  int nkt, nrb;
   static constexpr int g = 0;
-  __device__ __forceinline__ explicit SegWalk(const TileParams& p) : nkt(p.nkt) {}
-  __device__ __forceinline__ int cnt(int r) const { return SYM ? nkt - NQ * r : nkt; }
+  __device__ __forceinline__ explicit SegWalk(const TileParams& p) : nkt(p.nkt), nrb(p.nrb) {}
   // segment that starts at item `it`: row block, first key tile, number of key tiles
   __device__ __forceinline__ void locate(long long it, long long it_end, int& rb_out, int& j0, int& n) {
     if (SYM) {
-      while (it >= cum + cnt(rb)) {
-        cum += cnt(rb);
-        ++rb;
-      }
-      const int off = int(it - cum);
-      rb_out = rb;
-      j0 = NQ * rb + off;
-      n = int(min((long long)(cnt(rb) - off), it_end - it));
+      int off, cnt;
+      tri_locate<NQ>(it, nkt, nrb, rb_out, off, cnt);
+      j0 = NQ * rb_out + off;
+      n = int(min((long long)(cnt - off), it_end - it));
     } else {
       rb_out = int(it / nkt);
       j0 = int(it % nkt);
@@ -355,22 +371,23 @@ template <int NQ>
 struct GrpWalk {
   const TileParams& p;
   int g = 0;
-  int rb = 0;         // row block inside group g
-  long long cum = 0;  // items before (g, rb)
+  long long gbase = 0;  // items before group g
   __device__ __forceinline__ explicit GrpWalk(const TileParams& p_) : p(p_) {}
-  __device__ __forceinline__ int cnt() const { return g == 0 ? p.g_nkt[0] - NQ * rb : p.g_nkt[g]; }
   __device__ __forceinline__ void locate(long long it, long long it_end, int& rb_out, int& j0, int& n) {
-    while (it >= cum + cnt()) {
-      cum += cnt();
-      if (++rb * (128 * NQ) >= p.g_rows[g]) {
-        rb = 0;
-        ++g;
-      }
+    while (it >= gbase + p.g_items[g]) gbase += p.g_items[g++];
+    const long long idx = it - gbase;
+    int cnt, off;
+    if (g == 0) {
+      tri_locate<NQ>(idx, p.g_nkt[0], p.nrb, rb_out, off, cnt);
+      j0 = NQ * rb_out + off;
+    } else {
+      const int nk = p.g_nkt[g];
+      rb_out = int(idx / nk);
+      off = int(idx - (long long)rb_out * nk);
+      cnt = nk;
+      j0 = off;
     }
-    const int off = int(it - cum);
-    rb_out = rb;
-    j0 = (g == 0 ? NQ * rb : 0) + off;
-    n = int(min((long long)(cnt() - off), it_end - it));
+    n = int(min((long long)(cnt - off), it_end - it));
   }
 };
 
