@@ -21,10 +21,12 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     ok = True
     from maai_b200.Objective import peer_gather_available
-    modes = [False] + ([True] if peer_gather_available() else [])
+    # (peer gather?, cross-rank symmetric forward forced on / off)
+    modes = [(False, "0")] + ([(True, "0"), (True, "1")] if peer_gather_available() else [])
     if rank == 0:
-        print("gather modes under test (False = NCCL all_gather, True = fused NVLink peer stores):", modes)
-    for (b, d, tau), peer in [(c, m) for c in ((192, 128, 0.5), (1000, 64, 0.1), (512, 256, 0.2)) for m in modes]:
+        print("modes under test (peer: False = NCCL all_gather, True = fused NVLink peer stores; sym forward):", modes)
+    for (b, d, tau), (peer, sym) in [(c, m) for c in ((192, 128, 0.5), (1000, 64, 0.1), (512, 256, 0.2)) for m in modes]:
+        os.environ["MAAI_FWD_SYM_MULTI"] = sym
         g = torch.Generator().manual_seed(77)
         H1 = torch.randn(world * b, d, generator=g)
         H2 = H1 + 0.5 * torch.randn(world * b, d, generator=g)
@@ -48,7 +50,7 @@ def main():
                     l = res[kg][p][0]; g1 = res[kg][p][1:1 + b * d].reshape(b, d); g2 = res[kg][p][1 + b * d:].reshape(b, d)
                     e = (abs(l - ol[p]) / abs(ol[p]), np.linalg.norm(g1 - o1[p]) / np.linalg.norm(o1[p]),
                          np.linalg.norm(g2 - o2[p]) / np.linalg.norm(o2[p]))
-                    print(f"b={b} d={d} tau={tau} peer={peer} key_grad={kg} rank={p}: loss rel {e[0]:.2e} dh1 {e[1]:.2e} dh2 {e[2]:.2e}")
+                    print(f"b={b} d={d} tau={tau} peer={peer} sym={sym} key_grad={kg} rank={p}: loss rel {e[0]:.2e} dh1 {e[1]:.2e} dh2 {e[2]:.2e}")
                     ok = ok and e[0] <= 1e-3 and e[1] <= 1e-2 and e[2] <= 1e-2
             # full gradient / W == single-process reference on the concatenated batch
             gl, s1, s2 = O.contrastive_loss_oracle(H1.numpy(), H2.numpy(), tau)
