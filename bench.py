@@ -455,7 +455,7 @@ def main():
             "gpu_launches": int(main_r["launches"]),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["bf16"]) if achieved else None, "traffic": traffic,
-                         "traffic_note": "dram read+write bytes per launch, ncu --set full (profiles/r1_ncu_summary_v9.md): one pass "
+                         "traffic_note": "dram read+write bytes per launch, ncu --set full (profiles/r1_ncu_summary_v10.md): one pass "
                                          "over z (16.8 MB) + the fp32 accumulator lines the atomics touch (33.5 MB); the "
                                          "2Bx2B logits never reach HBM (the reference moves ~100*b*B bytes)",
                          "kernel": f"ntxent_tile_kernel<D={maai_b200.padded_dim(d)},BWD,NQ=1>",
