@@ -163,6 +163,17 @@ int maai_ntxent_bwd_dh(const float* dz_acc, const float* dz_extra, const float* 
                        const float* grad_loss, int b, int d, int d_pad, float inv_tau, int key_grad, int need_mask,
                        void* dh1, void* dh2, void* stream);
 
+/* Host-only views of the forward's tile schedule, for tests without a GPU (no CUDA call inside):
+ *   maai_debug_group_plan : the anchor groups rank `rank` computes in maai_ntxent_fwd_sym_tiles (arrays of
+ *                           9 entries): first anchor row (global), rows, key tiles, items of every group;
+ *                           group 0 is the rank's own triangular block
+ *   maai_debug_tri_locate : item `idx` of the folded triangular list of n_row_blocks row blocks over
+ *                           n_key_tiles key tiles (nq Q tiles per row block) -> row block, offset inside its
+ *                           segment, length of the segment */
+int maai_debug_group_plan(int b, int world, int rank, int d_pad, int* ngroups, int* qrow0, int* rows, int* nkt,
+                          long long* items);
+int maai_debug_tri_locate(long long idx, int n_key_tiles, int n_row_blocks, int nq, int* rb, int* off, int* cnt);
+
 /* Kernel launches enqueued by this library since load (bench.py's gpu_launches claim). */
 unsigned long long maai_launch_count(void);
 

@@ -45,6 +45,9 @@ SIGNATURES = {
     "maai_ntxent_bwd_dh": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int,
                                     _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_int, _c_int,
                                     _c_void_p, _c_void_p, _c_void_p]),
+    "maai_debug_group_plan": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                       _c_void_p]),
+    "maai_debug_tri_locate": (_c_int, [ctypes.c_longlong, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
     "maai_launch_count": (ctypes.c_ulonglong, []),
 }
 

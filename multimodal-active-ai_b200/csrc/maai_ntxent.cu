@@ -327,6 +327,42 @@ static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, f
 // Symmetric forward across ranks, tile part: this rank's own block (triangular) + the anchor groups
 // of the ranks "ahead" of it on the ring against its own keys (see maai_ntxent.h).
 extern "C++" {
+// Which tiles rank `rank` computes.  Group 0: its own block, triangular.  For dist = 1 .. world/2 the
+// anchors of q = rank + dist (mod world) against the local keys; the pair at distance world/2 (even
+// world) is split: the lower rank takes all of q's anchors against its first ceil(T/2) key tiles, the
+// higher rank takes the lower rank's anchors from row ceil(T/2)*128 on against all its keys.
+struct GroupPlan {
+  int ng = 0;
+  int qrow0[maai::kMaxGroups];   // first anchor row of the group (global row index)
+  int rows[maai::kMaxGroups];
+  int nkt[maai::kMaxGroups];
+  long long items[maai::kMaxGroups];
+  long long total = 0;
+};
+static GroupPlan plan_groups(int b, int world, int rank, int rb_rows, int nq) {
+  GroupPlan gp;
+  const int m_loc = 2 * b;
+  const int T = (m_loc + 127) / 128, Th = (T + 1) / 2;
+  const int nrb = (m_loc + rb_rows - 1) / rb_rows;
+  auto add = [&](int qrow0, int rows, int nkt) {
+    const int g = gp.ng++;
+    gp.qrow0[g] = qrow0;
+    gp.rows[g] = rows;
+    gp.nkt[g] = nkt;
+    gp.items[g] = g == 0 ? (long long)nrb * T - (long long)nq * nrb * (nrb - 1) / 2
+                         : (long long)((rows + rb_rows - 1) / rb_rows) * nkt;
+    gp.total += gp.items[g];
+  };
+  add(rank * m_loc, m_loc, T);
+  for (int dist = 1; 2 * dist <= world; ++dist) {
+    const int q = (rank + dist) % world;  // owner of the anchors
+    if (2 * dist < world) add(q * m_loc, m_loc, T);
+    else if (rank < q) add(q * m_loc, m_loc, Th);
+    else if (m_loc - Th * 128 > 0) add(q * m_loc + Th * 128, m_loc - Th * 128, T);
+  }
+  return gp;
+}
+
 template <int D, int NQ>
 static int launch_tile_groups(const void* z_glob, int b, int world, int rank, float inv_tau, float* rowsum_l,
                               float* stage, cudaStream_t s) {
@@ -356,32 +392,18 @@ static int launch_tile_groups(const void* z_glob, int b, int world, int rank, fl
   p.l_out = rowsum_l;
   p.pv_lbo = C::CHUNK_BYTES;
   p.pv_sbo = 1024;
-  const int T = p.nkt, Th = (T + 1) / 2;
-  int ng = 0;
-  long long total = (long long)p.nrb * T - (long long)NQ * p.nrb * (p.nrb - 1) / 2;
-  auto add = [&](int qrow0, int rows, int nkt, float* out) {
-    p.g_qrow0[ng] = qrow0;
-    p.g_rows[ng] = rows;
-    p.g_nkt[ng] = nkt;
-    p.g_out[ng] = out;
-    p.g_items[ng] = ng == 0 ? total : (long long)((rows + C::RB_ROWS - 1) / C::RB_ROWS) * nkt;
-    if (ng > 0) total += p.g_items[ng];
-    ++ng;
-  };
-  add(rank * m_loc, m_loc, T, rowsum_l);
-  for (int dist = 1; 2 * dist <= world; ++dist) {
-    const int q = (rank + dist) % world;  // owner of the anchors
-    float* out = stage + (size_t)q * m_loc;
-    if (2 * dist < world) {
-      add(q * m_loc, m_loc, T, out);
-    } else if (rank < q) {  // the pair at distance world/2 is split: lower rank takes its first key tiles
-      add(q * m_loc, m_loc, Th, out);
-    } else if (m_loc - Th * 128 > 0) {  // higher rank: the lower rank's anchors that are not among those keys
-      add(q * m_loc + Th * 128, m_loc - Th * 128, T, out + Th * 128);
-    }
+  const GroupPlan gp = plan_groups(b, world, rank, C::RB_ROWS, NQ);
+  for (int g = 0; g < gp.ng; ++g) {
+    p.g_qrow0[g] = gp.qrow0[g];
+    p.g_rows[g] = gp.rows[g];
+    p.g_nkt[g] = gp.nkt[g];
+    p.g_items[g] = gp.items[g];
+    // group 0: this rank's own row sums; others: slot of the anchors' owner in the staging vectors
+    p.g_out[g] = g == 0 ? rowsum_l : stage + gp.qrow0[g];  // stage is (world, 2b): indexed by global row
   }
-  p.ngroups = ng;
-  p.total_items = total;
+  p.ngroups = gp.ng;
+  p.total_items = gp.total;
+  const long long total = gp.total;
   int sms = sm_count();
   if (sms <= 0) return fail(MAAI_E_CUDA, "no CUDA device");
   const int grid = (int)(total < sms ? total : sms);
@@ -458,6 +480,32 @@ int maai_ntxent_fwd_sym_tiles(const void* z_glob, int b, int world, int rank, in
     case 256: return launch_tile_groups<256, 1>(z_glob, b, world, rank, inv_tau, rowsum_l, stage, s);
     default: return fail(MAAI_E_SHAPE, "d_pad must be 64, 128 or 256");
   }
+}
+
+int maai_debug_group_plan(int b, int world, int rank, int d_pad, int* ngroups, int* qrow0, int* rows, int* nkt,
+                          long long* items) {
+  if (!ngroups || !qrow0 || !rows || !nkt || !items) return fail(MAAI_E_ARG, "null pointer");
+  int rc = check_common(b, world, rank);
+  if (rc != MAAI_OK) return rc;
+  if (world > 2 * (maai::kMaxGroups - 1)) return fail(MAAI_E_SHAPE, "symmetric forward: world must be <= 16");
+  if (d_pad != 64 && d_pad != 128 && d_pad != 256) return fail(MAAI_E_SHAPE, "d_pad must be 64, 128 or 256");
+  const int nq = d_pad == 256 ? 1 : 2;
+  const GroupPlan gp = plan_groups(b, world, rank, 128 * nq, nq);
+  *ngroups = gp.ng;
+  for (int g = 0; g < gp.ng; ++g) {
+    qrow0[g] = gp.qrow0[g];
+    rows[g] = gp.rows[g];
+    nkt[g] = gp.nkt[g];
+    items[g] = gp.items[g];
+  }
+  return MAAI_OK;
+}
+
+int maai_debug_tri_locate(long long idx, int n_key_tiles, int n_row_blocks, int nq, int* rb, int* off, int* cnt) {
+  if (!rb || !off || !cnt || (nq != 1 && nq != 2)) return fail(MAAI_E_ARG, "bad argument");
+  if (nq == 1) maai::tri_locate<1>(idx, n_key_tiles, n_row_blocks, *rb, *off, *cnt);
+  else maai::tri_locate<2>(idx, n_key_tiles, n_row_blocks, *rb, *off, *cnt);
+  return MAAI_OK;
 }
 
 int maai_ntxent_fwd_sym_finalize(float* rowsum_l, const void* const* stage_bases, int b, int world, int rank,

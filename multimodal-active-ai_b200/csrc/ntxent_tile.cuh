@@ -326,7 +326,7 @@ __device__ __forceinline__ void softmax_chunk(uint32_t (&v)[CW], uint32_t (&pk)[
 // wherever it lies; in row-block order the last CTA collected all the short segments (21 of them at
 // 32768 pairs: each segment costs a Q-tile load + a pipeline refill, ~3-5 us).
 template <int NQ>
-__device__ __forceinline__ void tri_locate(long long idx, int T, int nrb, int& rb, int& off, int& cnt) {
+__host__ __device__ __forceinline__ void tri_locate(long long idx, int T, int nrb, int& rb, int& off, int& cnt) {
   const int S = 2 * T - NQ * (nrb - 1);
   const int pr = int(idx / S);
   const int r = int(idx - (long long)pr * S);

@@ -1,0 +1,91 @@
+"""Host-side logic of the forward's tile schedule, checked without a GPU through the library's host-only
+entry points (the same functions the kernels / launcher use):
+
+* ``maai_debug_tri_locate``: the folded triangular item list visits every (row block, key tile) on or
+  above the diagonal exactly once, segment by segment;
+* ``maai_debug_group_plan``: over all ranks, the anchor groups of the cross-rank symmetric forward cover
+  every unordered pair of global rows exactly once (so every row sum is complete and nothing is counted
+  twice), and the per-group item counts add up.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+
+def _lib():
+    from maai_b200 import _lib
+    return _lib, _lib.load()
+
+
+@pytest.mark.parametrize("T,nq", [(1, 1), (1, 2), (2, 2), (3, 2), (7, 1), (8, 2), (9, 2), (64, 2), (65, 2), (33, 1), (512, 2)])
+def test_folded_triangle_visits_every_tile_once(T, nq):
+    L, lib = _lib()
+    nrb = (T + nq - 1) // nq
+    total = nrb * T - nq * nrb * (nrb - 1) // 2
+    rb, off, cnt = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    seen = set()
+    it = 0
+    segments = []
+    while it < total:
+        L.check(lib.maai_debug_tri_locate(it, T, nrb, nq, ctypes.byref(rb), ctypes.byref(off), ctypes.byref(cnt)), "tri")
+        assert 0 <= rb.value < nrb and cnt.value == T - nq * rb.value and 0 <= off.value < cnt.value
+        # the kernel consumes the rest of the segment in one go
+        for o in range(off.value, cnt.value):
+            key = (rb.value, nq * rb.value + o)
+            assert key not in seen
+            seen.add(key)
+        segments.append((rb.value, cnt.value - off.value))
+        it += cnt.value - off.value
+    assert it == total
+    assert seen == {(r, k) for r in range(nrb) for k in range(nq * r, T)}
+    # folded order: consecutive pairs of segments hold the same number of items
+    if nrb >= 4:
+        pair = [segments[i][1] + segments[i + 1][1] for i in range(0, 2 * (nrb // 2), 2)]
+        assert len(set(pair)) == 1
+    # any item index inside a segment resolves to the same row block
+    for probe in np.linspace(0, total - 1, 17).astype(int):
+        L.check(lib.maai_debug_tri_locate(int(probe), T, nrb, nq, ctypes.byref(rb), ctypes.byref(off), ctypes.byref(cnt)), "tri")
+        assert (rb.value, nq * rb.value + off.value) in seen
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 5, 8, 16])
+@pytest.mark.parametrize("b,d_pad", [(64, 128), (96, 128), (200, 64), (130, 256), (512, 128)])
+def test_group_plan_covers_every_pair_once(world, b, d_pad):
+    L, lib = _lib()
+    m = 2 * b
+    M = m * world
+    nq = 1 if d_pad == 256 else 2
+    rb_rows = 128 * nq
+    T = (m + 127) // 128
+    count = np.zeros((M, M), dtype=np.int32)
+    for rank in range(world):
+        ng = ctypes.c_int()
+        q0 = (ctypes.c_int * 9)(); rows = (ctypes.c_int * 9)(); nkt = (ctypes.c_int * 9)()
+        items = (ctypes.c_longlong * 9)()
+        L.check(lib.maai_debug_group_plan(b, world, rank, d_pad, ctypes.byref(ng), q0, rows, nkt, items), "plan")
+        assert 1 <= ng.value <= 9
+        # group 0: own block, triangular -> every pair inside the slot once (both orders by symmetry)
+        assert (q0[0], rows[0], nkt[0]) == (rank * m, m, T)
+        nrb = (m + rb_rows - 1) // rb_rows
+        assert items[0] == nrb * T - nq * nrb * (nrb - 1) // 2
+        lo = rank * m
+        count[lo:lo + m, lo:lo + m] += 1
+        for g in range(1, ng.value):
+            a0, ar, kt = q0[g], rows[g], nkt[g]
+            assert ar > 0 and 0 < kt <= T and a0 // m != rank and (a0 % m) + ar <= m  # inside ONE other slot
+            assert items[g] == ((ar + rb_rows - 1) // rb_rows) * kt
+            k1 = min(kt * 128, m)  # local keys [0, k1)
+            # E_ak serves anchor a's row sum (staged for its owner) and key k's row sum (local column sum)
+            count[a0:a0 + ar, lo:lo + k1] += 1
+            count[lo:lo + k1, a0:a0 + ar] += 1
+    assert (count == 1).all(), np.argwhere(count != 1)[:5]
+
+
+def test_group_plan_rejects_bad_arguments():
+    L, lib = _lib()
+    ng = ctypes.c_int()
+    q0 = (ctypes.c_int * 9)(); rows = (ctypes.c_int * 9)(); nkt = (ctypes.c_int * 9)(); items = (ctypes.c_longlong * 9)()
+    assert lib.maai_debug_group_plan(64, 17, 0, 128, ctypes.byref(ng), q0, rows, nkt, items) == -2
+    assert lib.maai_debug_group_plan(64, 4, 4, 128, ctypes.byref(ng), q0, rows, nkt, items) == -1
+    assert lib.maai_debug_group_plan(64, 4, 0, 100, ctypes.byref(ng), q0, rows, nkt, items) == -2
