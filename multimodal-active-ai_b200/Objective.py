@@ -194,8 +194,8 @@ def _sym_forward_enabled(b, dp, world) -> bool:
     """Cross-rank symmetric forward (peer mode only).  A tile that serves a row AND a column costs 1.29x
     a plain one, the split adds a barrier and a second small kernel (~30 us): measured at 32768 pairs,
     d=128 it wins at 2 ranks (forward 0.54 -> 0.43 ms, step 1.44 -> 1.30 ms), is marginal at 4 (step 0.732
-    -> 0.718 ms) and a wash at 8 (0.145 vs 0.155 ms), so it is used from 16384 rows per rank up.  MAAI_FWD_SYM_MULTI=1 / 0 force
-    it on / off; at most 16 ranks (group table of the kernel)."""
+    -> 0.718 ms) and a wash at 8 (0.145 vs 0.155 ms), so it is used from 16384 rows per rank up.
+    MAAI_FWD_SYM_MULTI=1 / 0 force it on / off; at most 16 ranks (group table of the kernel)."""
     v = os.environ.get("MAAI_FWD_SYM_MULTI", "")
     if v == "0" or world > 16:
         return False
