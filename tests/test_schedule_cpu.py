@@ -89,3 +89,16 @@ def test_group_plan_rejects_bad_arguments():
     assert lib.maai_debug_group_plan(64, 17, 0, 128, ctypes.byref(ng), q0, rows, nkt, items) == -2
     assert lib.maai_debug_group_plan(64, 4, 4, 128, ctypes.byref(ng), q0, rows, nkt, items) == -1
     assert lib.maai_debug_group_plan(64, 4, 0, 100, ctypes.byref(ng), q0, rows, nkt, items) == -2
+
+
+def test_cross_rank_symmetric_forward_switch(monkeypatch):
+    """Every rank must take the same decision from (b, d_pad, world) and the environment alone."""
+    from maai_b200.Objective import _sym_forward_enabled
+    monkeypatch.delenv("MAAI_FWD_SYM_MULTI", raising=False)
+    assert _sym_forward_enabled(16384, 128, 2) and _sym_forward_enabled(8192, 128, 4)
+    assert not _sym_forward_enabled(4096, 128, 8)
+    assert not _sym_forward_enabled(1 << 20, 128, 17)  # group table of the kernel: world <= 16
+    monkeypatch.setenv("MAAI_FWD_SYM_MULTI", "1")
+    assert _sym_forward_enabled(64, 128, 8) and not _sym_forward_enabled(64, 128, 32)
+    monkeypatch.setenv("MAAI_FWD_SYM_MULTI", "0")
+    assert not _sym_forward_enabled(16384, 128, 2)
