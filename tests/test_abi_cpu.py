@@ -45,6 +45,20 @@ def test_c_abi_argument_errors_without_gpu():
     assert lib.maai_ntxent_normalize(None, None, 4, 8, 0, None, None, None, None) == _lib.E_ARG
     assert b"null" in lib.maai_last_error()
     assert lib.maai_ntxent_fwd(None, 4, 1, 0, 64, 1.0, None, None, None, None, None) == _lib.E_ARG
+    # the later entry points validate the same way (ABI v4 / v5)
+    assert lib.maai_ntxent_bwd_tiles(None, None, None, 4, 1, 0, 64, 1.0, 3, None, None) == _lib.E_ARG
+    assert lib.maai_ntxent_bwd_keyside(None, None, 4, 2, 0, 64, 1.0, None, None) == _lib.E_ARG
+    assert lib.maai_ntxent_bwd_dh(None, None, None, None, None, None, 0, None, None, 4, 8, 64, 1.0, 1, 3,
+                                  None, None, None) == _lib.E_ARG
+    assert lib.maai_ntxent_fwd_sym_tiles(None, 4, 2, 0, 64, 1.0, None, None, None) == _lib.E_ARG
+    assert lib.maai_ntxent_fwd_sym_finalize(None, None, 4, 2, 0, 1.0, None, None, None, None, None, None) == _lib.E_ARG
+    import ctypes
+    buf = (ctypes.c_float * 64)()
+    ptr = ctypes.cast(buf, ctypes.c_void_p)
+    # bad rank / world / width with non-null pointers: still no CUDA call
+    assert lib.maai_ntxent_fwd_sym_tiles(ptr, 4, 2, 2, 64, 1.0, ptr, ptr, None) == _lib.E_ARG
+    assert lib.maai_ntxent_fwd_sym_tiles(ptr, 4, 17, 0, 64, 1.0, ptr, ptr, None) == _lib.E_SHAPE
+    assert lib.maai_ntxent_bwd_keyside(ptr, ptr, 4, 2, 0, 96, 1.0, ptr, None) == _lib.E_SHAPE
     with pytest.raises(ValueError):
         _lib.check(_lib.E_SHAPE, "x")
     with pytest.raises(_lib.MaaiError):
