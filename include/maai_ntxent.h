@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MAAI_ABI_VERSION 5
+#define MAAI_ABI_VERSION 6
 
 #define MAAI_OK 0
 #define MAAI_E_ARG (-1)
@@ -44,6 +44,22 @@ const char* maai_last_error(void);
 /* Padded embedding width used by the tile kernels: 64, 128 or 256; MAAI_E_SHAPE if d < 1 or d > 256. */
 int maai_padded_dim(int d);
 
+/* Step workspace (optional, caller-owned; SURVEY.md section 8b "no allocation inside the C ABI"): one
+ * 16-byte aligned fp32 region that K1 zero-fills (its zero_fill argument), so that the step needs no
+ * memset / zero kernel and the forward can finish its per-row tail inside the tile kernel:
+ *   words [0, 2b)                       rowsum_l
+ *   words [2b, 2b + MAAI_WS_CTL_WORDS)  control words (word 0: CTA-done counter of the forward)
+ *   words [head, head + 2b*d_pad)       dz_acc, only with need_bwd; head = 2b + 32 rounded up to 128
+ * Pass its base as rowsum_l to the forward and base + head as dz_acc to the backward, both with
+ * MAAI_F_PREZEROED.  Returns 0 for an unsupported shape. */
+#define MAAI_WS_CTL_WORDS 32
+#define MAAI_F_PREZEROED 1
+size_t maai_ntxent_workspace_bytes(int b, int d_pad, int need_bwd);
+
+/* 1 if maai_ntxent_fwd will run the symmetric (upper-triangle) tile schedule for this shape: single rank
+ * only, by size, MAAI_FWD_SYM=0/1 forces.  Reporting / tests; the result is the same either way. */
+int maai_ntxent_fwd_is_symmetric(int b, int world, int d_pad);
+
 /* Number of floats the `r_glob` array of maai_ntxent_bwd must hold: world*2b rounded up to 128. */
 size_t maai_ntxent_r_len(int b, int world);
 
@@ -53,9 +69,11 @@ size_t maai_ntxent_r_len(int b, int world);
  *   z_out      (2b, d_pad) bf16: rows [0,b) = normalised h1, rows [b,2b) = normalised h2; pass the
  *              address of this rank's slot of the (world, 2b, d_pad) gather buffer
  *   inv_norm   (2b) fp32   1 / max(||h||, 1e-12)
- *   pos_cos    (b)  fp32   cosine of each positive pair computed from the bf16 rows */
+ *   pos_cos    (b)  fp32   cosine of each positive pair computed from the bf16 rows
+ *   zero_fill  optional (NULL / 0): 16-byte aligned region of zero_bytes bytes (multiple of 4) that the
+ *              kernel zero-fills on the side: the step workspace above */
 int maai_ntxent_normalize(const void* h1, const void* h2, int b, int d, int in_dtype, void* z_out,
-                          float* inv_norm, float* pos_cos, void* stream);
+                          float* inv_norm, float* pos_cos, void* zero_fill, size_t zero_bytes, void* stream);
 
 /* K2 -- replaces the four matmuls, /temperature, the LARGE_NUM self-mask, cat + log_softmax and the
  * masked sum (Objective.py:67-79, 123-125) for this rank's 2b anchor rows against all world*2b keys.
@@ -64,9 +82,13 @@ int maai_ntxent_normalize(const void* h1, const void* h2, int b, int d, int in_d
  *   rowsum_l   (2b) out: l'_i = sum over the NEGATIVES j (j != i, j != pos(i)) of exp((z_i.z_j - 1)/tau);
  *              the positive's term e_pos = exp((pos_cos - 1)/tau) is added in fp32 where needed
  *   r_out      (2b) out, may be NULL: 1 / (b * (e_pos + l'_i)), the row factor the backward needs
- *   loss_out   (1)  out: this rank's loss, exactly Objective.py:79 */
+ *   loss_out   (1)  out: this rank's loss, exactly Objective.py:79
+ *   flags      0: rowsum_l is zeroed inside (one more launch) and the per-row tail (loss, r) is a separate
+ *              finalize launch.  MAAI_F_PREZEROED: rowsum_l is the base of a step workspace that K1 has
+ *              zero-filled; no zero launch, and up to 32768 rows the LAST CTA of the tile kernel to finish
+ *              runs the per-row tail itself (one launch for the whole forward). */
 int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
-                    const float* pos_cos, float* rowsum_l, float* r_out, float* loss_out,
+                    const float* pos_cos, float* rowsum_l, float* r_out, float* loss_out, int flags,
                     void* stream);
 
 /* K1 fused with the cross-replica embedding gather (replaces Objective.py:41-43 AND :52-53, 102-114):
@@ -79,7 +101,7 @@ int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, f
  *                 row is stored ONCE and the NVSwitch replicates it into every rank's buffer */
 int maai_ntxent_normalize_peer(const void* h1, const void* h2, int b, int d, int in_dtype,
                                const void* const* peer_z_bases, void* mc_z_base, int world, int rank,
-                               float* inv_norm, float* pos_cos, void* stream);
+                               float* inv_norm, float* pos_cos, void* zero_fill, size_t zero_bytes, void* stream);
 
 /* K2 fused with the all-gather of the row factors: like maai_ntxent_fwd, but r_i is stored into slot
  * `rank` of every rank's gathered r array (maai_ntxent_r_len floats each, zero padded by the owner).
@@ -87,7 +109,7 @@ int maai_ntxent_normalize_peer(const void* h1, const void* h2, int b, int d, int
  *   mc_r_base     multicast address of the r arrays, or NULL */
 int maai_ntxent_fwd_peer(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
                          const float* pos_cos, float* rowsum_l, const void* const* peer_r_bases,
-                         void* mc_r_base, float* loss_out, void* stream);
+                         void* mc_r_base, float* loss_out, int flags, void* stream);
 
 /* K2 across ranks with the symmetry of E (world > 1): E_ij = E_ji, so every (anchor slot, key slot)
  * pair of ranks needs its tiles computed ONCE.  Rank p computes its own block (the tiles on / above the
@@ -101,7 +123,7 @@ int maai_ntxent_fwd_peer(const void* z_glob, int b, int world, int rank, int d_p
  *   stage_bases  device array of `world` addresses: every rank's `stage`, as mapped into this process
  *   r_out        (2b) or NULL;  peer_r_bases / mc_r_base as in maai_ntxent_fwd_peer, or NULL */
 int maai_ntxent_fwd_sym_tiles(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
-                              float* rowsum_l, float* stage, void* stream);
+                              float* rowsum_l, float* stage, int flags /* MAAI_F_PREZEROED: rowsum_l */, void* stream);
 int maai_ntxent_fwd_sym_finalize(float* rowsum_l, const void* const* stage_bases, int b, int world, int rank,
                                  float inv_tau, const float* pos_cos, float* r_out,
                                  const void* const* peer_r_bases, void* mc_r_base, float* loss_out,
@@ -133,11 +155,13 @@ int maai_ntxent_fwd_eval(const void* z_glob, int b, int world, int rank, int d_p
  *   need_mask  bit 0: dh1 wanted, bit 1: dh2 wanted (hidden1 is detached in the reference's
  *              training loop, Contrastive_Learning.py:685)
  *   dh1, dh2   (b, d) dtype in_dtype, written only when the matching bit is set (may be NULL otherwise)
- *   dz_acc     (2b, d_pad) fp32 scratch */
+ *   dz_acc     (2b, d_pad) fp32 scratch
+ *   flags      0: dz_acc is zeroed inside (one more launch); MAAI_F_PREZEROED: the caller (K1's zero_fill)
+ *              has zeroed it */
 int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, int key_grad,
                     const float* rowsum_l, const float* pos_cos, const void* h1, const void* h2, int in_dtype,
                     const float* inv_norm, const float* grad_loss, int b, int world, int rank, int d, int d_pad,
-                    float inv_tau, int need_mask, void* dh1, void* dh2, float* dz_acc, void* stream);
+                    float inv_tau, int need_mask, void* dh1, void* dh2, float* dz_acc, int flags, void* stream);
 
 /* The backward in its three pieces, for the key-side REDUCE-SCATTER dataflow (SURVEY.md section 7 /
  * BASELINE.json north_star): instead of using the symmetry of E (maai_ntxent_bwd, key_grad = 1), every

@@ -71,14 +71,46 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-def _stream() -> int:
-    # raw handle of the current stream of the current device (torch.cuda.current_stream() builds a
+def _stream(dev: Optional[torch.device] = None) -> int:
+    # raw handle of the current stream of the tensors' device (torch.cuda.current_stream() builds a
     # Python Stream object and costs ~10 us per call; three calls per step were 1/4 of the host time
     # at small batches)
+    idx = torch.cuda.current_device() if dev is None or dev.index is None else dev.index
     try:
-        return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+        return torch._C._cuda_getCurrentRawStream(idx)
     except AttributeError:  # pragma: no cover - older / newer torch without the private hook
-        return torch.cuda.current_stream().cuda_stream
+        return torch.cuda.current_stream(idx).cuda_stream
+
+
+class _on_device:
+    """The C ABI launches on the CURRENT CUDA device: make that the tensors' device for the duration of
+    the calls (a no-op, and no context-manager cost, in the one-process-per-GPU case)."""
+
+    def __init__(self, dev: torch.device):
+        self.guard = None
+        if dev.index is not None and dev.index != torch.cuda.current_device():
+            self.guard = torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
+        return False
+
+
+def _step_workspace(lib, b: int, dp: int, need_bwd: bool, dev):
+    """The step's fp32 scratch (include/maai_ntxent.h "step workspace"): row sums, control words and -- if a
+    backward will follow -- the dz accumulator, ONE allocation that K1 zero-fills on the side, so the step
+    has no memset / zero kernels and the forward finalizes inside its tile kernel."""
+    nbytes = lib.maai_ntxent_workspace_bytes(b, dp, 1 if need_bwd else 0)
+    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+    head = (2 * b + _lib.WS_CTL_WORDS + 127) // 128 * 128
+    dz_acc = ws[head:head + 2 * b * dp].view(2 * b, dp) if need_bwd else None
+    return ws, ws[:2 * b], dz_acc
 
 
 def padded_dim(d: int) -> int:
@@ -118,12 +150,21 @@ class PeerWorkspace:
     every rank's buffer, followed by a symmetric-memory barrier (~7 us).  Memory comes from
     torch.distributed._symmetric_memory (plumbing: allocation, handle exchange, barrier).
 
-    Two buffer sets are used alternately: set i of step t is overwritten by step t+2, which a rank can
-    reach only after every peer has passed the barriers of step t+1, i.e. has finished reading step t.
-    A backward that finds its set overwritten (more than two forwards in flight) raises.
+    Buffer reuse across ranks.  NBUF = 3 sets are used in turn.  A peer may write set i (its K1 /
+    finalize stores of step t) as soon as IT has passed the barriers of step t-1; the readers of the set's
+    previous contents (step u = t-3) on THIS rank are the forward of u -- stream-ordered before this
+    rank's barriers of step u+1 -- and the backward of u.  So the set may be reused iff every rank issued
+    its backward of u before its last barrier of step t-1.  Every rank runs the same program (they meet in
+    the barriers, or deadlock), so each rank decides from its own issue order, identically:
+      * backward of u issued before the forward of t-1 (f b f b ..., or two steps in flight
+        f0 f1 b1 b0 f2 f3 b3 b2: what three sets buy): nothing to do;
+      * backward of u issued later, but before this forward: one extra barrier in front of K1 orders it;
+      * backward of u still outstanding (more than NBUF-1 forwards in flight): RuntimeError at the forward
+        -- never a silent overwrite; ``peer_gather=False`` (NCCL path, private buffers) has no limit.
+    Forward-only calls (no_grad) never have a backward outstanding.
     """
     _cache = {}
-    NBUF = 2
+    NBUF = 3
 
     def __init__(self, b, dp, world, rank, device, group):
         import torch.distributed._symmetric_memory as symm_mem
@@ -162,8 +203,9 @@ class PeerWorkspace:
             mc = 0
         self.mc_z = [mc + o if mc else None for o in self.off_z]
         self.mc_r = [mc + o if mc else None for o in self.off_r]
-        self.gen = [0] * self.NBUF
-        self.step = 0
+        self.step = 0                                    # forwards issued so far
+        self.bwd_pending = [False] * self.NBUF           # set's last forward still waits for its backward
+        self.bwd_stamp = [-1] * self.NBUF                # self.step at the time that backward was issued
         torch.cuda.synchronize(device)
         self.hdl.barrier(channel=0)                      # every rank's zero fill is done before first use
 
@@ -180,11 +222,28 @@ class PeerWorkspace:
             ws = cls._cache[key] = cls(b, dp, world, rank, device, group)
         return ws
 
-    def next_set(self):
-        i = self.step % self.NBUF
-        self.step += 1
-        self.gen[i] += 1
-        return i, self.gen[i]
+    def next_set(self, needs_bwd: bool):
+        """Set for the forward being issued (see the class docstring for the reuse rule).  Returns
+        (set index, extra_barrier): extra_barrier = a barrier must precede this forward's first store."""
+        t = self.step
+        i = t % self.NBUF
+        if self.bwd_pending[i]:
+            raise RuntimeError(
+                f"maai NT-Xent: {self.NBUF} forward passes through the peer-gather workspace are waiting for "
+                f"their backward; at most {self.NBUF - 1} may be in flight (the next forward would overwrite "
+                "buffers a backward still reads, on this or another rank). Call backward first, or pass "
+                "peer_gather=False to use the NCCL all-gather path")
+        # the set's previous backward was issued after the forward of step t-1 had been issued: the peers'
+        # barriers of step t-1 do not cover it
+        extra = self.bwd_stamp[i] >= t
+        self.step = t + 1
+        self.bwd_pending[i] = bool(needs_bwd)
+        self.bwd_stamp[i] = -1
+        return i, extra
+
+    def backward_issued(self, i: int):
+        self.bwd_pending[i] = False
+        self.bwd_stamp[i] = self.step
 
 
 _peer_state = {"ok": None}
@@ -269,42 +328,46 @@ class _NTXentFunction(torch.autograd.Function):
         full = (bool(key_grad) and not rs) or world == 1
         ctx.rs_group = group if rs else None
         ctx.rs = rs
-        if peer and world > 1:
-            return _NTXentFunction._forward_peer(ctx, h1, h2, dt, inv_tau, rank, world, group, needs_grad, full,
-                                                 stash)
-        z_all = torch.empty((world, 2 * b, dp), dtype=torch.bfloat16, device=dev)
-        # one allocation for the small fp32 outputs (each torch.empty is ~3 us of host time)
-        small = torch.empty(5 * b + 4, dtype=torch.float32, device=dev)
-        inv_norm = small[:2 * b]
-        rowsum = small[2 * b:4 * b]
-        pos_cos = small[4 * b:5 * b]
-        loss = small[5 * b:5 * b + 1].view(())
-        r_len = lib.maai_ntxent_r_len(b, world)
-        r_col = torch.zeros(r_len, dtype=torch.float32, device=dev) if needs_grad else None
-        if needs_grad and full:
-            r_row = r_col[rank * 2 * b:(rank + 1) * 2 * b]  # this rank's slot of the gathered factors
-        elif needs_grad:
-            r_row = torch.empty(2 * b, dtype=torch.float32, device=dev)  # keys detached: r_col stays 0
-        else:
-            r_row = None
+        with _on_device(dev):
+            if peer and world > 1:
+                return _NTXentFunction._forward_peer(ctx, h1, h2, dt, inv_tau, rank, world, group, needs_grad,
+                                                     full, stash)
+            st = _stream(dev)
+            z_all = torch.empty((world, 2 * b, dp), dtype=torch.bfloat16, device=dev)
+            ws, rowsum, dz_acc = _step_workspace(lib, b, dp, needs_grad, dev)
+            # one allocation for the small fp32 outputs (each torch.empty is ~3 us of host time)
+            small = torch.empty(3 * b + 4, dtype=torch.float32, device=dev)
+            inv_norm = small[:2 * b]
+            pos_cos = small[2 * b:3 * b]
+            loss = small[3 * b:3 * b + 1].view(())
+            r_len = lib.maai_ntxent_r_len(b, world)
+            r_col = torch.zeros(r_len, dtype=torch.float32, device=dev) if needs_grad else None
+            if needs_grad and full:
+                r_row = r_col[rank * 2 * b:(rank + 1) * 2 * b]  # this rank's slot of the gathered factors
+            elif needs_grad:
+                r_row = torch.empty(2 * b, dtype=torch.float32, device=dev)  # keys detached: r_col stays 0
+            else:
+                r_row = None
 
-        with _Profiler.span("normalize"):
-            _lib.check(lib.maai_ntxent_normalize(_ptr(h1), _ptr(h2), b, d, dt, _ptr(z_all[rank]),
-                                                 _ptr(inv_norm), _ptr(pos_cos), _stream()),
-                       "maai_ntxent_normalize")
-        with _Profiler.span("gather_z"):
-            gather_rows(z_all, rank, group)
-        with _Profiler.span("fwd"):
-            _lib.check(lib.maai_ntxent_fwd(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(pos_cos),
-                                           _ptr(rowsum), _ptr(r_row), _ptr(loss), _stream()),
-                       "maai_ntxent_fwd")
-        if needs_grad:
-            if full:
-                with _Profiler.span("gather_r"):
-                    gather_row_factors(r_col, rank, b, world, group)
-            ctx.save_for_backward(h1, h2, z_all, inv_norm, r_row, r_col, pos_cos, rowsum)
-            ctx.cfg = (b, d, dp, dt, inv_tau, rank, world, full)
-            ctx.peer = None
+            with _Profiler.span("normalize"):
+                _lib.check(lib.maai_ntxent_normalize(_ptr(h1), _ptr(h2), b, d, dt, _ptr(z_all[rank]),
+                                                     _ptr(inv_norm), _ptr(pos_cos), _ptr(ws), ws.numel() * 4, st),
+                           "maai_ntxent_normalize")
+            with _Profiler.span("gather_z"):
+                gather_rows(z_all, rank, group)
+            with _Profiler.span("fwd"):
+                _lib.check(lib.maai_ntxent_fwd(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(pos_cos),
+                                               _ptr(rowsum), _ptr(r_row), _ptr(loss), _lib.F_PREZEROED, st),
+                           "maai_ntxent_fwd")
+            if needs_grad:
+                if full:
+                    with _Profiler.span("gather_r"):
+                        gather_row_factors(r_col, rank, b, world, group)
+                ctx.save_for_backward(h1, h2, z_all, inv_norm, r_row, r_col, pos_cos, rowsum)
+                ctx.cfg = (b, d, dp, dt, inv_tau, rank, world, full)
+                ctx.peer = None
+                ctx.dz_acc = dz_acc
+                ctx.acc_clean = True   # zero-filled by K1; a second backward (retain_graph) zeroes it itself
         if stash is not None:
             stash["z_all"] = z_all
             stash["rowsum"] = rowsum
@@ -318,16 +381,21 @@ class _NTXentFunction(torch.autograd.Function):
         b, d = h1.shape
         dev = h1.device
         dp = padded_dim(d)
+        st = _stream(dev)
         ws = PeerWorkspace.get(b, dp, world, rank, dev, group)
-        i, gen = ws.next_set()
+        i, extra_barrier = ws.next_set(needs_grad)
         z_all = ws.z[i]
-        inv_norm = torch.empty(2 * b, dtype=torch.float32, device=dev)
-        pos_cos = torch.empty(b, dtype=torch.float32, device=dev)
-        rowsum = torch.empty(2 * b, dtype=torch.float32, device=dev)
-        loss = torch.empty((), dtype=torch.float32, device=dev)
+        wsp, rowsum, dz_acc = _step_workspace(lib, b, dp, needs_grad, dev)
+        small = torch.empty(3 * b + 4, dtype=torch.float32, device=dev)
+        inv_norm = small[:2 * b]
+        pos_cos = small[2 * b:3 * b]
+        loss = small[3 * b:3 * b + 1].view(())
+        if extra_barrier:  # the previous user of this set ran its backward late: see PeerWorkspace
+            ws.hdl.barrier(channel=0)
         with _Profiler.span("normalize"):
             _lib.check(lib.maai_ntxent_normalize_peer(_ptr(h1), _ptr(h2), b, d, dt, _ptr(ws.z_tab[i]), ws.mc_z[i],
-                                                      world, rank, _ptr(inv_norm), _ptr(pos_cos), _stream()),
+                                                      world, rank, _ptr(inv_norm), _ptr(pos_cos), _ptr(wsp),
+                                                      wsp.numel() * 4, st),
                        "maai_ntxent_normalize_peer")
         with _Profiler.span("gather_z"):
             ws.hdl.barrier(channel=0)  # every rank's rows have landed in every buffer
@@ -342,25 +410,27 @@ class _NTXentFunction(torch.autograd.Function):
             # peers' staging vectors after a barrier
             with _Profiler.span("fwd"):
                 _lib.check(lib.maai_ntxent_fwd_sym_tiles(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(rowsum),
-                                                         _ptr(ws.stage[i]), _stream()), "maai_ntxent_fwd_sym_tiles")
+                                                         _ptr(ws.stage[i]), _lib.F_PREZEROED, st),
+                           "maai_ntxent_fwd_sym_tiles")
             with _Profiler.span("gather_l"):
                 ws.hdl.barrier(channel=2)
             with _Profiler.span("finalize"):
                 _lib.check(lib.maai_ntxent_fwd_sym_finalize(_ptr(rowsum), _ptr(ws.s_tab[i]), b, world, rank, inv_tau,
                                                             _ptr(pos_cos), _ptr(r_row),
                                                             _ptr(ws.r_tab[i]) if peer_r else None,
-                                                            ws.mc_r[i] if peer_r else None, _ptr(loss), _stream()),
+                                                            ws.mc_r[i] if peer_r else None, _ptr(loss), st),
                            "maai_ntxent_fwd_sym_finalize")
         else:
             with _Profiler.span("fwd"):
                 if peer_r:
                     _lib.check(lib.maai_ntxent_fwd_peer(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(pos_cos),
                                                         _ptr(rowsum), _ptr(ws.r_tab[i]), ws.mc_r[i], _ptr(loss),
-                                                        _stream()),
+                                                        _lib.F_PREZEROED, st),
                                "maai_ntxent_fwd_peer")
                 else:
                     _lib.check(lib.maai_ntxent_fwd(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(pos_cos),
-                                                   _ptr(rowsum), _ptr(r_row), _ptr(loss), _stream()), "maai_ntxent_fwd")
+                                                   _ptr(rowsum), _ptr(r_row), _ptr(loss), _lib.F_PREZEROED, st),
+                               "maai_ntxent_fwd")
         if needs_grad:
             if full:
                 with _Profiler.span("gather_r"):
@@ -369,7 +439,9 @@ class _NTXentFunction(torch.autograd.Function):
                 r_row = r_col[rank * 2 * b:(rank + 1) * 2 * b]
             ctx.save_for_backward(h1, h2, z_all, inv_norm, r_row, r_col, pos_cos, rowsum)
             ctx.cfg = (b, d, dp, dt, inv_tau, rank, world, full)
-            ctx.peer = (ws, i, gen)
+            ctx.peer = (ws, i)
+            ctx.dz_acc = dz_acc
+            ctx.acc_clean = True
         if stash is not None:
             stash["z_all"] = z_all
             stash["rowsum"] = rowsum
@@ -381,27 +453,29 @@ class _NTXentFunction(torch.autograd.Function):
         lib = _lib.load()
         h1, h2, z_all, inv_norm, r_row, r_col, pos_cos, rowsum = ctx.saved_tensors
         b, d, dp, dt, inv_tau, rank, world, full = ctx.cfg
-        if ctx.peer is not None:
-            ws, i, gen = ctx.peer
-            if ws.gen[i] != gen:
-                raise RuntimeError("maai NT-Xent: the peer workspace of this forward pass has been overwritten "
-                                   "(more than two forward passes in flight before backward); pass "
-                                   "peer_gather=False to use the NCCL all-gather path")
         need = (1 if ctx.needs_input_grad[0] else 0) | (2 if ctx.needs_input_grad[1] else 0)
         dev = h1.device
         g = grad_loss.to(device=dev, dtype=torch.float32).contiguous()
         dh1 = torch.empty_like(h1) if need & 1 else None
         dh2 = torch.empty_like(h2) if need & 2 else None
-        dz_acc = torch.empty((2 * b, dp), dtype=torch.float32, device=dev)
-        if ctx.rs:
-            return _NTXentFunction._backward_reduce_scatter(ctx, g, need, dh1, dh2, dz_acc)
-        with _Profiler.span("bwd"):
-            _lib.check(lib.maai_ntxent_bwd(_ptr(z_all), _ptr(r_row), _ptr(r_col), 1 if full else 0,
-                                           _ptr(rowsum), _ptr(pos_cos), _ptr(h1), _ptr(h2), dt, _ptr(inv_norm),
-                                           _ptr(g), b, world, rank, d, dp, inv_tau, need, _ptr(dh1),
-                                           _ptr(dh2), _ptr(dz_acc), _stream()),
-                       "maai_ntxent_bwd")
-        return dh1, dh2, None, None, None, None, None, None, None
+        dz_acc = ctx.dz_acc
+        flags = _lib.F_PREZEROED if ctx.acc_clean else 0
+        ctx.acc_clean = False
+        with _on_device(dev):
+            if ctx.rs:
+                out = _NTXentFunction._backward_reduce_scatter(ctx, g, need, dh1, dh2, dz_acc)
+            else:
+                with _Profiler.span("bwd"):
+                    _lib.check(lib.maai_ntxent_bwd(_ptr(z_all), _ptr(r_row), _ptr(r_col), 1 if full else 0,
+                                                   _ptr(rowsum), _ptr(pos_cos), _ptr(h1), _ptr(h2), dt, _ptr(inv_norm),
+                                                   _ptr(g), b, world, rank, d, dp, inv_tau, need, _ptr(dh1),
+                                                   _ptr(dh2), _ptr(dz_acc), flags, _stream(dev)),
+                               "maai_ntxent_bwd")
+                out = (dh1, dh2, None, None, None, None, None, None, None)
+        if ctx.peer is not None:
+            ws, i = ctx.peer
+            ws.backward_issued(i)  # the set's readers are all on the stream now (PeerWorkspace reuse rule)
+        return out
 
 
 def _backward_reduce_scatter(ctx, g, need, dh1, dh2, dz_acc):
@@ -412,23 +486,24 @@ def _backward_reduce_scatter(ctx, g, need, dh1, dh2, dz_acc):
     h1, h2, z_all, inv_norm, r_row, r_col, pos_cos, rowsum = ctx.saved_tensors
     b, d, dp, dt, inv_tau, rank, world, _ = ctx.cfg
     dev = h1.device
+    st = _stream(dev)
     r_pad = torch.zeros(lib.maai_ntxent_r_len(b, 1), dtype=torch.float32, device=dev)
     r_pad[:2 * b].copy_(r_row)
     dz_keys = torch.empty((world * 2 * b, dp), dtype=torch.float32, device=dev)
     dz_mine = torch.empty((2 * b, dp), dtype=torch.float32, device=dev)
     with _Profiler.span("bwd_keyside"):
         _lib.check(lib.maai_ntxent_bwd_keyside(_ptr(z_all), _ptr(r_pad), b, world, rank, dp, inv_tau,
-                                               _ptr(dz_keys), _stream()), "maai_ntxent_bwd_keyside")
+                                               _ptr(dz_keys), st), "maai_ntxent_bwd_keyside")
     work = dist.reduce_scatter_tensor(dz_mine, dz_keys, group=ctx.rs_group, async_op=True)
     with _Profiler.span("bwd"):
         _lib.check(lib.maai_ntxent_bwd_tiles(_ptr(z_all), _ptr(r_row), _ptr(r_col), b, world, rank, dp, inv_tau,
-                                             need, _ptr(dz_acc), _stream()), "maai_ntxent_bwd_tiles")
+                                             need, _ptr(dz_acc), st), "maai_ntxent_bwd_tiles")
     with _Profiler.span("reduce_scatter_wait"):
         work.wait()
     with _Profiler.span("bwd_dh"):
         _lib.check(lib.maai_ntxent_bwd_dh(_ptr(dz_acc), _ptr(dz_mine), _ptr(rowsum), _ptr(pos_cos), _ptr(h1),
                                           _ptr(h2), dt, _ptr(inv_norm), _ptr(g), b, d, dp, inv_tau, 1, need,
-                                          _ptr(dh1), _ptr(dh2), _stream()), "maai_ntxent_bwd_dh")
+                                          _ptr(dh1), _ptr(dh2), st), "maai_ntxent_bwd_dh")
     return dh1, dh2, None, None, None, None, None, None, None
 
 
@@ -450,12 +525,14 @@ def _forward_eval(hidden1, hidden2, temperature, rank, world, group):
     rowsum = torch.empty(2 * b, dtype=torch.float32, device=dev)
     loss = torch.empty((), dtype=torch.float32, device=dev)
     ranks = torch.empty(b, dtype=torch.int32, device=dev)
-    _lib.check(lib.maai_ntxent_normalize(_ptr(h1), _ptr(h2), b, d, _DTYPES[h1.dtype], _ptr(z_all[rank]),
-                                         _ptr(inv_norm), _ptr(pos_cos), _stream()), "maai_ntxent_normalize")
-    gather_rows(z_all, rank, group)
-    _lib.check(lib.maai_ntxent_fwd_eval(_ptr(z_all), b, world, rank, dp, 1.0 / float(temperature),
-                                        _ptr(pos_cos), _ptr(rowsum), _ptr(loss), _ptr(ranks), _stream()),
-               "maai_ntxent_fwd_eval")
+    with _on_device(dev):
+        st = _stream(dev)
+        _lib.check(lib.maai_ntxent_normalize(_ptr(h1), _ptr(h2), b, d, _DTYPES[h1.dtype], _ptr(z_all[rank]),
+                                             _ptr(inv_norm), _ptr(pos_cos), None, 0, st), "maai_ntxent_normalize")
+        gather_rows(z_all, rank, group)
+        _lib.check(lib.maai_ntxent_fwd_eval(_ptr(z_all), b, world, rank, dp, 1.0 / float(temperature),
+                                            _ptr(pos_cos), _ptr(rowsum), _ptr(loss), _ptr(ranks), st),
+                   "maai_ntxent_fwd_eval")
     return loss, ranks
 
 
@@ -482,8 +559,18 @@ def _validate(hidden1, hidden2, hidden_norm, temperature, world_size, local_rank
         raise ValueError("empty batch")
 
 
+_warned = set()
+
+
+def _warn_once(key: str, msg: str) -> None:
+    if key not in _warned:
+        _warned.add(key)
+        import warnings
+        warnings.warn(msg, stacklevel=3)
+
+
 def contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0, local_rank=0, world_size=1,
-                     device="cpu", *, group=None, key_grad=True, return_logits=None, fused_topk=False,
+                     device="cpu", *, group=None, key_grad=None, return_logits=None, fused_topk=False,
                      peer_gather=None, _stash=None):
     """Drop-in for Objective.contrastive_loss (Objective.py:17-81).
 
@@ -492,7 +579,11 @@ def contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0, local_
     Extra keyword-only args: ``group`` process group for the gathers; ``key_grad`` see module doc
       (True: full gradient via the symmetry of E, no gradient collective; False: the reference's
       query-side-only gradient; "reduce_scatter": the same full gradient computed as key-side partial
-      sums + ``dist.reduce_scatter_tensor`` -- kept for comparison, 1.5x the tensor-core work);
+      sums + ``dist.reduce_scatter_tensor`` -- kept for comparison, 1.5x the tensor-core work).
+      Default None = True; with ``world_size > 1`` that is NOT what the reference computes -- its
+      ``dist.all_gather`` is non-differentiable (Objective.py:112-114), so an unmodified multi-GPU run
+      trains on the query-side half only (about half the gradient norm at the same learning rate) -- so the
+      first such call warns once; pass ``key_grad=True`` / ``False`` explicitly to choose (INTEGRATION.md);
       ``return_logits`` force (True) / suppress (False) the (logits_ab, labels) outputs, default:
       only when autograd is disabled (the validate() path).
       ``peer_gather`` (world_size > 1): True = the two gathers of the path are fused into the producing
@@ -509,6 +600,15 @@ def contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0, local_
     Returns (loss, logits_ab, labels) like the reference.
     """
     _validate(hidden1, hidden2, hidden_norm, temperature, world_size, local_rank)
+    if key_grad is None:
+        key_grad = True
+        if int(world_size) > 1 and torch.is_grad_enabled() and (hidden1.requires_grad or hidden2.requires_grad):
+            _warn_once("key_grad", "maai NT-Xent: world_size > 1 with the default key_grad=True yields the FULL "
+                       "gradient (query + key side; after DDP's 1/W it equals the single-process reference on the "
+                       "global batch). The reference's own multi-GPU branch drops the key-side half "
+                       "(non-differentiable dist.all_gather, Objective.py:112-114): pass key_grad=False to "
+                       "reproduce it, or key_grad=True to silence this warning (see INTEGRATION.md on the "
+                       "learning-rate implication)")
     if hidden1.dtype != hidden2.dtype:
         # e.g. hidden1 = outputs1.data kept from an autocast forward, hidden2 fp32: compute in the wider
         # type like the reference's F.normalize / matmul type promotion would
@@ -599,7 +699,7 @@ class GraphedNTXentLoss(torch.nn.Module):
 class NTXentLoss(torch.nn.Module):
     """Module form of :func:`contrastive_loss` holding temperature / rank / world / group."""
 
-    def __init__(self, temperature=1.0, local_rank=0, world_size=1, group=None, key_grad=True):
+    def __init__(self, temperature=1.0, local_rank=0, world_size=1, group=None, key_grad=None):
         super().__init__()
         self.temperature = float(temperature)
         self.local_rank = int(local_rank)

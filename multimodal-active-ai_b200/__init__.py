@@ -3,7 +3,7 @@
 The directory name carries a hyphen (repo convention); import it through the ``maai_b200`` shim at
 the repo root:  ``import maai_b200; maai_b200.contrastive_loss(...)``.
 """
-from . import _lib  # noqa: F401
+from . import Model_Util, _lib  # noqa: F401
 from .Model_Util import top_k_accuracy  # noqa: F401
 from .Objective import LARGE_NUM, GraphedNTXentLoss, NTXentLoss, contrastive_loss, padded_dim  # noqa: F401
 

@@ -9,7 +9,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # MAAI_DEBUG_LIB selects an A/B build of the same library (tools/ab_variants.py); never a fallback
 LIB_PATH = os.environ.get("MAAI_DEBUG_LIB") or os.path.join(HERE, "libmaai_ntxent.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
+F_PREZEROED = 1
+WS_CTL_WORDS = 32
 OK, E_ARG, E_SHAPE, E_CUDA = 0, -1, -2, -3
 DT_F32, DT_BF16, DT_F16 = 0, 1, 2
 
@@ -21,21 +23,23 @@ SIGNATURES = {
     "maai_last_error": (ctypes.c_char_p, []),
     "maai_padded_dim": (_c_int, [_c_int]),
     "maai_ntxent_r_len": (_c_size_t, [_c_int, _c_int]),
+    "maai_ntxent_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
+    "maai_ntxent_fwd_is_symmetric": (_c_int, [_c_int, _c_int, _c_int]),
     "maai_ntxent_normalize": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p,
-                                       _c_void_p, _c_void_p, _c_void_p]),
+                                       _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "maai_ntxent_fwd": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p,
-                                 _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+                                 _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p]),
     "maai_ntxent_normalize_peer": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
-                                            _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p]),
+                                            _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "maai_ntxent_fwd_peer": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p,
-                                      _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+                                      _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p]),
     "maai_ntxent_fwd_eval": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p,
                                       _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "maai_ntxent_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                  _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
-                                 _c_float, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+                                 _c_float, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p]),
     "maai_ntxent_fwd_sym_tiles": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p,
-                                           _c_void_p]),
+                                           _c_int, _c_void_p]),
     "maai_ntxent_fwd_sym_finalize": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p,
                                               _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "maai_ntxent_bwd_tiles": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float,

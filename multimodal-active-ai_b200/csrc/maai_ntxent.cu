@@ -103,20 +103,38 @@ int zero_words(void* p, size_t n_words, cudaStream_t s) {
   size_t blocks = (n_words / 4 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 592) blocks = 592;
-  --g_launches;  // bookkeeping kernels are not counted in gpu_launches (they replaced memsets)
   cudaError_t e = launch_k(maai::zero_kernel, dim3((unsigned)blocks), dim3(256), 0, s, static_cast<uint32_t*>(p), n_words);
   if (e != cudaSuccess) return cuda_fail("zero_kernel", e);
   return MAAI_OK;
 }
 
+constexpr int kMaxDevices = 64;
+int current_device() {
+  int dev = 0;
+  return cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxDevices ? dev : -1;
+}
+// SM count of the CURRENT device (cached per device ordinal: one process may drive several GPUs)
 int sm_count() {
-  static int n = [] {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  static std::atomic<int> cache[kMaxDevices];
+  const int dev = current_device();
+  if (dev < 0) return 0;
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
     if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    return v;
-  }();
-  return n;
+    cache[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per (kernel, device)
+template <typename K>
+cudaError_t ensure_smem_attr(K kernel, int bytes, std::atomic<unsigned long long>& done_mask) {
+  const int dev = current_device();
+  if (dev < 0) return cudaErrorInvalidDevice;
+  const unsigned long long bit = 1ull << dev;
+  if (done_mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done_mask.fetch_or(bit, std::memory_order_release);
+  return e;
 }
 
 struct RankArgs {
@@ -124,6 +142,9 @@ struct RankArgs {
   int* rank_out = nullptr;
   int pos_period = 0;  // anchors spanning several rank slots (maai_ntxent_bwd_tiles)
   int pos_phase = 0;
+  // forward: in-kernel finalize by the last CTA (null done_ctr = separate finalize launch)
+  unsigned int* done_ctr = nullptr;
+  maai::FinalizeArgs fin = {};
 };
 
 template <int D, bool BWD, int NQ, bool RANK = false, bool SYM = false>
@@ -131,18 +152,16 @@ int launch_tile(const void* q_base, int m_loc, const void* k_base, int m_glob, i
                 float inv_tau, const float* r_row, const float* r_col, float* l_out, float* dz_acc,
                 int pos_split, int pos_delta, cudaStream_t s, RankArgs ra = RankArgs()) {
   using C = maai::TileCfg<D, BWD, NQ>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(maai::ntxent_tile_kernel<D, BWD, NQ, RANK, SYM>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-  });
+  static std::atomic<unsigned long long> attr_done{0};
+  cudaError_t attr_err = ensure_smem_attr(maai::ntxent_tile_kernel<D, BWD, NQ, RANK, SYM>, C::SMEM_BYTES, attr_done);
   if (attr_err != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(smem)", attr_err);
   CUtensorMap tq, tk;
   int rc;
   if ((rc = make_rows_tmap(&tq, q_base, m_loc, D)) != MAAI_OK) return rc;
   if ((rc = make_rows_tmap(&tk, k_base, m_glob, D)) != MAAI_OK) return rc;
-  maai::TileParams p;
+  maai::TileParams p{};
+  p.done_ctr = ra.done_ctr;
+  p.fin = ra.fin;
   p.m_loc = m_loc;
   p.m_glob = m_glob;
   p.row_global_base = row_global_base;
@@ -233,56 +252,127 @@ size_t maai_ntxent_r_len(int b, int world) {
   return (m + 127) / 128 * 128;
 }
 
-int maai_ntxent_normalize(const void* h1, const void* h2, int b, int d, int in_dtype, void* z_out,
-                          float* inv_norm, float* pos_cos, void* stream) {
-  if (!h1 || !h2 || !z_out || !inv_norm || !pos_cos) return fail(MAAI_E_ARG, "null pointer");
+size_t maai_ntxent_workspace_bytes(int b, int d_pad, int need_bwd) {
+  if (b < 1 || (d_pad != 64 && d_pad != 128 && d_pad != 256)) return 0;
+  const size_t head = ((size_t)2 * b + MAAI_WS_CTL_WORDS + 127) / 128 * 128;  // row sums + control words
+  return (head + (need_bwd ? (size_t)2 * b * d_pad : 0)) * sizeof(float);
+}
+
+int maai_ntxent_fwd_is_symmetric(int b, int world, int d_pad) {
+  // Single rank: anchors == keys and E_ij = E_ji, so only the tiles on and above the diagonal are
+  // computed (half the MMAs and exp2s; measured forward 0.955 -> 0.724 ms at 32768 pairs, d=128).
+  // d_pad = 256 below 8192 pairs: the triangular item list cuts a CTA's range into several short
+  // segments, each with its own 64 KB Q-tile load (measured 0.17 -> 0.27 ms per step at 4096 pairs).
+  // MAAI_FWD_SYM=1 / 0 force it on / off (read per call: the parity tests run both).
+  if (world != 1 || env_int("MAAI_DEBUG_FWD_NQ", 2) != 2) return 0;
+  const int v = env_int("MAAI_FWD_SYM", -1);
+  if (v == 0 || v == 1) return v;
+  return (d_pad <= 128 || 2 * b >= 16384) ? 1 : 0;
+}
+
+// K1 in all its forms: local slot and / or peer / multicast stores, optional zero fill
+static int normalize_impl(const void* h1, const void* h2, int b, int d, int in_dtype, void* z_local,
+                          const void* const* peer_z_bases, void* mc_z_base, int world, int rank, float* inv_norm,
+                          float* pos_cos, void* zero_fill, size_t zero_bytes, cudaStream_t s) {
+  if (!h1 || !h2 || !inv_norm || !pos_cos) return fail(MAAI_E_ARG, "null pointer");
   if (b < 1) return fail(MAAI_E_ARG, "b must be >= 1");
   const int dp = maai_padded_dim(d);
   if (dp < 0) return fail(MAAI_E_SHAPE, "embedding dim must be in [1, 256]");
-  if (!aligned16(z_out)) return fail(MAAI_E_ARG, "z_out must be 16-byte aligned");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (z_local && !aligned16(z_local)) return fail(MAAI_E_ARG, "z_out must be 16-byte aligned");
+  if (zero_bytes && (!zero_fill || !aligned16(zero_fill) || (zero_bytes & 3)))
+    return fail(MAAI_E_ARG, "zero_fill must be 16-byte aligned and zero_bytes a multiple of 4");
   const int wpb = 8;
   const int grid = (b + wpb - 1) / wpb;
-  auto* z = static_cast<__nv_bfloat16*>(z_out);
-  cudaError_t e;
-  switch (in_dtype) {
-    case MAAI_DT_F32:
-      e = launch_k(maai::normalize_cast_kernel<float>, dim3(grid), dim3(wpb * 32), 0, s,
-                   static_cast<const float*>(h1), static_cast<const float*>(h2), b, d, dp, z, inv_norm, pos_cos);
-      break;
-    case MAAI_DT_BF16:
-      e = launch_k(maai::normalize_cast_kernel<__nv_bfloat16>, dim3(grid), dim3(wpb * 32), 0, s,
-                   static_cast<const __nv_bfloat16*>(h1), static_cast<const __nv_bfloat16*>(h2), b, d, dp, z,
-                   inv_norm, pos_cos);
-      break;
-    case MAAI_DT_F16:
-      e = launch_k(maai::normalize_cast_kernel<__half>, dim3(grid), dim3(wpb * 32), 0, s,
-                   static_cast<const __half*>(h1), static_cast<const __half*>(h2), b, d, dp, z, inv_norm, pos_cos);
-      break;
-    default:
-      return fail(MAAI_E_ARG, "in_dtype must be MAAI_DT_F32, MAAI_DT_BF16 or MAAI_DT_F16");
+  const auto* pb = reinterpret_cast<const unsigned long long*>(peer_z_bases);
+  const size_t esz = in_dtype == MAAI_DT_F32 ? 4 : 2;
+  const int vec = dp / 32;
+  // vector loads need every row chunk aligned: d a multiple of the chunk and aligned base addresses
+  const bool vec_ok = (d % vec) == 0 && (reinterpret_cast<uintptr_t>(h1) % (vec * esz)) == 0 &&
+                      (reinterpret_cast<uintptr_t>(h2) % (vec * esz)) == 0;
+  cudaError_t e = cudaSuccess;
+#define MAAI_K1(T, V)                                                                                          \
+  e = launch_k(maai::normalize_cast_kernel<T, V>, dim3(grid), dim3(wpb * 32), 0, s, static_cast<const T*>(h1), \
+               static_cast<const T*>(h2), b, d, vec_ok, static_cast<__nv_bfloat16*>(z_local), pb,              \
+               reinterpret_cast<unsigned long long>(mc_z_base), world, rank, inv_norm, pos_cos,                 \
+               static_cast<uint32_t*>(zero_fill), zero_bytes / 4)
+#define MAAI_K1_DP(T)               \
+  switch (dp) {                     \
+    case 64: MAAI_K1(T, 2); break;  \
+    case 128: MAAI_K1(T, 4); break; \
+    default: MAAI_K1(T, 8); break;  \
   }
+  switch (in_dtype) {
+    case MAAI_DT_F32: MAAI_K1_DP(float); break;
+    case MAAI_DT_BF16: MAAI_K1_DP(__nv_bfloat16); break;
+    case MAAI_DT_F16: MAAI_K1_DP(__half); break;
+    default: return fail(MAAI_E_ARG, "in_dtype must be MAAI_DT_F32, MAAI_DT_BF16 or MAAI_DT_F16");
+  }
+#undef MAAI_K1_DP
+#undef MAAI_K1
   MAAI_CUDA(e);
   return MAAI_OK;
 }
 
+int maai_ntxent_normalize(const void* h1, const void* h2, int b, int d, int in_dtype, void* z_out,
+                          float* inv_norm, float* pos_cos, void* zero_fill, size_t zero_bytes, void* stream) {
+  if (!z_out) return fail(MAAI_E_ARG, "null pointer");
+  return normalize_impl(h1, h2, b, d, in_dtype, z_out, nullptr, nullptr, 1, 0, inv_norm, pos_cos, zero_fill,
+                        zero_bytes, static_cast<cudaStream_t>(stream));
+}
+
+static maai::FinalizeArgs make_fin(float* rowsum_l, const float* pos_cos, int b, float inv_tau, float* r_out,
+                                   float* loss_out, const void* const* peer_r, int world, int rank, void* mc_r,
+                                   const void* const* stage_bases) {
+  maai::FinalizeArgs f;
+  f.l = rowsum_l;
+  f.pos_cos = pos_cos;
+  f.b = b;
+  f.inv_tau = inv_tau;
+  f.r_out = r_out;
+  f.loss_out = loss_out;
+  f.peer_r = reinterpret_cast<const unsigned long long*>(peer_r);
+  f.world = world;
+  f.my_rank = rank;
+  f.mc_r = static_cast<float*>(mc_r);
+  f.stage_tab = reinterpret_cast<const unsigned long long*>(stage_bases);
+  return f;
+}
+
+// Rows up to which the forward's per-row tail runs inside the tile kernel (last CTA done) instead of
+// as a separate 8-CTA cluster launch: one CTA needs ~0.15 us per 1000 rows more than the cluster, a
+// launch costs 3-5 us of gap + prologue.  MAAI_TAIL_FINALIZE_ROWS overrides (0 = never).
+static int tail_finalize_rows() {
+  static const int v = env_int("MAAI_TAIL_FINALIZE_ROWS", 32768);
+  return v;
+}
+
 static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
                     const float* pos_cos, float* rowsum_l, float* r_out, float* loss_out,
-                    int* pos_rank, void* stream, const void* const* peer_r = nullptr, void* mc_r = nullptr) {
+                    int* pos_rank, int flags, void* stream, const void* const* peer_r = nullptr,
+                    void* mc_r = nullptr) {
   if (!z_glob || !pos_cos || !rowsum_l || !loss_out) return fail(MAAI_E_ARG, "null pointer");
   int rc = check_common(b, world, rank);
   if (rc != MAAI_OK) return rc;
   if (!(inv_tau > 0.f)) return fail(MAAI_E_ARG, "temperature must be positive");
   if (!aligned16(z_glob)) return fail(MAAI_E_ARG, "z_glob must be 16-byte aligned");
+  if (flags & ~MAAI_F_PREZEROED) return fail(MAAI_E_ARG, "unknown flag");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int m_loc = 2 * b, m_glob = 2 * b * world;
-  if ((rc = zero_words(rowsum_l, (size_t)m_loc, s)) != MAAI_OK) return rc;
+  const bool prezeroed = flags & MAAI_F_PREZEROED;  // rowsum_l = head of a step workspace K1 has zero-filled
+  if (!prezeroed && (rc = zero_words(rowsum_l, (size_t)m_loc, s)) != MAAI_OK) return rc;
   const char* q_base = static_cast<const char*>(z_glob) + (size_t)rank * m_loc * d_pad * 2;
+  const maai::FinalizeArgs fin =
+      make_fin(rowsum_l, pos_cos, b, inv_tau, r_out, loss_out, peer_r, world, rank, mc_r, nullptr);
+  RankArgs ra;
+  const bool tail = prezeroed && !pos_rank && m_loc <= tail_finalize_rows();
+  if (tail) {
+    ra.done_ctr = reinterpret_cast<unsigned int*>(rowsum_l + m_loc);  // control word 0 of the workspace
+    ra.fin = fin;
+  }
   if (pos_rank) {
     // evaluation forward: same kernel + the rank of every view-a anchor's positive among the
     // view-b keys (one instantiation per padded width, the forward's default tile layout)
     if ((rc = zero_words(pos_rank, (size_t)b, s)) != MAAI_OK) return rc;
-    RankArgs ra;
     ra.pos_cos = pos_cos;
     ra.rank_out = pos_rank;
 #define MAAI_LAUNCH_RANK(DD, NQQ)                                                                   \
@@ -295,32 +385,25 @@ static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, f
       default: return fail(MAAI_E_SHAPE, "d_pad must be 64, 128 or 256");
     }
 #undef MAAI_LAUNCH_RANK
-  } else if (world == 1 && env_int("MAAI_DEBUG_FWD_NQ", 2) == 2 &&
-             (env_int("MAAI_FWD_SYM", -1) == 1 ||
-              // d_pad = 256 below 8192 pairs: the triangular item list cuts a CTA's range into several short
-              // segments, each with its own 64 KB Q-tile load (measured 0.17 -> 0.27 ms per step at 4096 pairs)
-              (env_int("MAAI_FWD_SYM", -1) == -1 && (d_pad <= 128 || m_loc >= 16384)))) {
-    // Single rank: anchors == keys and E_ij = E_ji, so only the tiles on and above the diagonal are
-    // computed; a tile above it adds its row sums to the anchors and its column sums to the keys
-    // (half the MMAs and exp2s; measured forward 0.955 -> 0.724 ms at 32768 pairs, d=128, 0.884 -> 0.726
-    // at d=64, step -12.6 % under sustained load; MAAI_FWD_SYM=0 selects the full-tile forward).
+  } else if (maai_ntxent_fwd_is_symmetric(b, world, d_pad)) {
+    // a tile above the diagonal adds its row sums to the anchors and its column sums to the keys
     if (d_pad == 64)
       rc = launch_tile<64, false, 2, false, true>(q_base, m_loc, z_glob, m_glob, 0, inv_tau, nullptr, nullptr,
-                                                  rowsum_l, nullptr, b, b, s);
+                                                  rowsum_l, nullptr, b, b, s, ra);
     else if (d_pad == 128)
       rc = launch_tile<128, false, 2, false, true>(q_base, m_loc, z_glob, m_glob, 0, inv_tau, nullptr, nullptr,
-                                                   rowsum_l, nullptr, b, b, s);
-    else  // one Q tile per row block: row tile rb visits key tiles kt >= rb
+                                                   rowsum_l, nullptr, b, b, s, ra);
+    else if (d_pad == 256)  // one Q tile per row block: row tile rb visits key tiles kt >= rb
       rc = launch_tile<256, false, 1, false, true>(q_base, m_loc, z_glob, m_glob, 0, inv_tau, nullptr, nullptr,
-                                                   rowsum_l, nullptr, b, b, s);
+                                                   rowsum_l, nullptr, b, b, s, ra);
+    else
+      return fail(MAAI_E_SHAPE, "d_pad must be 64, 128 or 256");
   } else {
     rc = dispatch_tile<false>(d_pad, q_base, m_loc, z_glob, m_glob, rank * m_loc, inv_tau, nullptr,
-                              nullptr, rowsum_l, nullptr, b, b, s);
+                              nullptr, rowsum_l, nullptr, b, b, s, ra);
   }
   if (rc != MAAI_OK) return rc;
-  MAAI_CUDA(launch_k(maai::finalize_loss_kernel, dim3(maai::kFinalizeCluster), dim3(1024), 0, s, rowsum_l,
-                     pos_cos, b, inv_tau, r_out, loss_out, reinterpret_cast<const unsigned long long*>(peer_r),
-                     world, rank, static_cast<float*>(mc_r), static_cast<const unsigned long long*>(nullptr)));
+  if (!tail) MAAI_CUDA(launch_k(maai::finalize_loss_kernel, dim3(maai::kFinalizeCluster), dim3(1024), 0, s, fin));
   return MAAI_OK;
 }
 
@@ -367,12 +450,9 @@ template <int D, int NQ>
 static int launch_tile_groups(const void* z_glob, int b, int world, int rank, float inv_tau, float* rowsum_l,
                               float* stage, cudaStream_t s) {
   using C = maai::TileCfg<D, false, NQ>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(maai::ntxent_tile_kernel<D, false, NQ, false, true, true>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-  });
+  static std::atomic<unsigned long long> attr_done{0};
+  cudaError_t attr_err =
+      ensure_smem_attr(maai::ntxent_tile_kernel<D, false, NQ, false, true, true>, C::SMEM_BYTES, attr_done);
   if (attr_err != cudaSuccess) return cuda_fail("cudaFuncSetAttribute(smem)", attr_err);
   const int m_loc = 2 * b, m_glob = 2 * b * world;
   const char* k_base = static_cast<const char*>(z_glob) + (size_t)rank * m_loc * D * 2;
@@ -414,57 +494,33 @@ static int launch_tile_groups(const void* z_glob, int b, int world, int rank, fl
 }  // extern "C++"
 
 int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
-                    const float* pos_cos, float* rowsum_l, float* r_out, float* loss_out,
+                    const float* pos_cos, float* rowsum_l, float* r_out, float* loss_out, int flags,
                     void* stream) {
-  return fwd_impl(z_glob, b, world, rank, d_pad, inv_tau, pos_cos, rowsum_l, r_out, loss_out, nullptr,
+  return fwd_impl(z_glob, b, world, rank, d_pad, inv_tau, pos_cos, rowsum_l, r_out, loss_out, nullptr, flags,
                   stream);
 }
 
 int maai_ntxent_normalize_peer(const void* h1, const void* h2, int b, int d, int in_dtype,
                                const void* const* peer_z_bases, void* mc_z_base, int world, int rank,
-                               float* inv_norm, float* pos_cos, void* stream) {
-  if (!h1 || !h2 || !peer_z_bases || !inv_norm || !pos_cos) return fail(MAAI_E_ARG, "null pointer");
+                               float* inv_norm, float* pos_cos, void* zero_fill, size_t zero_bytes, void* stream) {
+  if (!peer_z_bases) return fail(MAAI_E_ARG, "null pointer");
   int rc = check_common(b, world, rank);
   if (rc != MAAI_OK) return rc;
-  const int dp = maai_padded_dim(d);
-  if (dp < 0) return fail(MAAI_E_SHAPE, "embedding dim must be in [1, 256]");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int wpb = 8;
-  const int grid = (b + wpb - 1) / wpb;
-  const auto* pb = reinterpret_cast<const unsigned long long*>(peer_z_bases);
-  cudaError_t e = cudaSuccess;
-#define MAAI_K1P(T, V)                                                                            \
-  e = launch_k(maai::normalize_cast_peer_kernel<T, V>, dim3(grid), dim3(wpb * 32), 0, s,          \
-               static_cast<const T*>(h1), static_cast<const T*>(h2), b, d, pb,                     \
-               reinterpret_cast<unsigned long long>(mc_z_base), world, rank, inv_norm, pos_cos)
-#define MAAI_K1P_DP(T)          \
-  switch (dp) {                 \
-    case 64: MAAI_K1P(T, 2); break;  \
-    case 128: MAAI_K1P(T, 4); break; \
-    default: MAAI_K1P(T, 8); break;  \
-  }
-  switch (in_dtype) {
-    case MAAI_DT_F32: MAAI_K1P_DP(float); break;
-    case MAAI_DT_BF16: MAAI_K1P_DP(__nv_bfloat16); break;
-    case MAAI_DT_F16: MAAI_K1P_DP(__half); break;
-    default: return fail(MAAI_E_ARG, "in_dtype must be MAAI_DT_F32, MAAI_DT_BF16 or MAAI_DT_F16");
-  }
-#undef MAAI_K1P_DP
-#undef MAAI_K1P
-  MAAI_CUDA(e);
-  return MAAI_OK;
+  return normalize_impl(h1, h2, b, d, in_dtype, nullptr, peer_z_bases, mc_z_base, world, rank, inv_norm, pos_cos,
+                        zero_fill, zero_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int maai_ntxent_fwd_peer(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
                          const float* pos_cos, float* rowsum_l, const void* const* peer_r_bases,
-                         void* mc_r_base, float* loss_out, void* stream) {
+                         void* mc_r_base, float* loss_out, int flags, void* stream) {
   if (!peer_r_bases) return fail(MAAI_E_ARG, "null pointer");
-  return fwd_impl(z_glob, b, world, rank, d_pad, inv_tau, pos_cos, rowsum_l, nullptr, loss_out, nullptr,
+  return fwd_impl(z_glob, b, world, rank, d_pad, inv_tau, pos_cos, rowsum_l, nullptr, loss_out, nullptr, flags,
                   stream, peer_r_bases, mc_r_base);
 }
 
 int maai_ntxent_fwd_sym_tiles(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
-                              float* rowsum_l, float* stage, void* stream) {
+                              float* rowsum_l, float* stage, int flags, void* stream) {
+  if (flags & ~MAAI_F_PREZEROED) return fail(MAAI_E_ARG, "unknown flag");
   if (!z_glob || !rowsum_l || !stage) return fail(MAAI_E_ARG, "null pointer");
   int rc = check_common(b, world, rank);
   if (rc != MAAI_OK) return rc;
@@ -472,7 +528,7 @@ int maai_ntxent_fwd_sym_tiles(const void* z_glob, int b, int world, int rank, in
   if (!(inv_tau > 0.f)) return fail(MAAI_E_ARG, "temperature must be positive");
   if (!aligned16(z_glob)) return fail(MAAI_E_ARG, "z_glob must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if ((rc = zero_words(rowsum_l, (size_t)2 * b, s)) != MAAI_OK) return rc;
+  if (!(flags & MAAI_F_PREZEROED) && (rc = zero_words(rowsum_l, (size_t)2 * b, s)) != MAAI_OK) return rc;
   if ((rc = zero_words(stage, (size_t)2 * b * world, s)) != MAAI_OK) return rc;
   switch (d_pad) {
     case 64: return launch_tile_groups<64, 2>(z_glob, b, world, rank, inv_tau, rowsum_l, stage, s);
@@ -517,10 +573,9 @@ int maai_ntxent_fwd_sym_finalize(float* rowsum_l, const void* const* stage_bases
   if (rc != MAAI_OK) return rc;
   if (!(inv_tau > 0.f)) return fail(MAAI_E_ARG, "temperature must be positive");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  MAAI_CUDA(launch_k(maai::finalize_loss_kernel, dim3(maai::kFinalizeCluster), dim3(1024), 0, s, rowsum_l,
-                     pos_cos, b, inv_tau, r_out, loss_out,
-                     reinterpret_cast<const unsigned long long*>(peer_r_bases), world, rank,
-                     static_cast<float*>(mc_r_base), reinterpret_cast<const unsigned long long*>(stage_bases)));
+  MAAI_CUDA(launch_k(maai::finalize_loss_kernel, dim3(maai::kFinalizeCluster), dim3(1024), 0, s,
+                     make_fin(rowsum_l, pos_cos, b, inv_tau, r_out, loss_out, peer_r_bases, world, rank, mc_r_base,
+                              stage_bases)));
   return MAAI_OK;
 }
 
@@ -528,20 +583,21 @@ int maai_ntxent_fwd_eval(const void* z_glob, int b, int world, int rank, int d_p
                          const float* pos_cos, float* rowsum_l, float* loss_out, int* pos_rank,
                          void* stream) {
   if (!pos_rank) return fail(MAAI_E_ARG, "null pointer");
-  return fwd_impl(z_glob, b, world, rank, d_pad, inv_tau, pos_cos, rowsum_l, nullptr, loss_out, pos_rank,
+  return fwd_impl(z_glob, b, world, rank, d_pad, inv_tau, pos_cos, rowsum_l, nullptr, loss_out, pos_rank, 0,
                   stream);
 }
 
 // tile pass of the backward over this rank's anchors: zeroes the accumulator rows, then K3
 static int bwd_tiles_impl(const void* z_glob, const float* r_row, const float* r_col, int b, int world, int rank,
-                          int d_pad, float inv_tau, int need_mask, float* dz_acc, cudaStream_t s) {
+                          int d_pad, float inv_tau, int need_mask, float* dz_acc, cudaStream_t s,
+                          bool prezeroed = false) {
   const int m_loc = 2 * b, m_glob = 2 * b * world;
   // anchor rows that need a gradient: both views, or one contiguous view
   const int row_begin = (need_mask == 2) ? b : 0;
   const int rows = (need_mask == 3) ? m_loc : b;
   float* acc = dz_acc + (size_t)row_begin * d_pad;
   int rc;
-  if ((rc = zero_words(acc, (size_t)rows * d_pad, s)) != MAAI_OK) return rc;
+  if (!prezeroed && (rc = zero_words(acc, (size_t)rows * d_pad, s)) != MAAI_OK) return rc;
   const char* q_base =
       static_cast<const char*>(z_glob) + ((size_t)rank * m_loc + row_begin) * d_pad * 2;
   return dispatch_tile<true>(d_pad, q_base, rows, z_glob, m_glob, rank * m_loc + row_begin, inv_tau,
@@ -555,29 +611,29 @@ static int bwd_dh_impl(const float* dz_acc, const float* dz_extra, const float* 
   const int rows = (need_mask == 3) ? 2 * b : b;
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
-  cudaError_t e;
-  switch (in_dtype) {
-    case MAAI_DT_F32:
-      e = launch_k(maai::dh_kernel<float>, dim3(grid), dim3(wpb * 32), 0, s, dz_acc, dz_extra,
-                   static_cast<const float*>(h1), static_cast<const float*>(h2), inv_norm, grad_loss, rowsum_l,
-                   pos_cos, b, d, d_pad, inv_tau, key_grad, need_mask, static_cast<float*>(dh1),
-                   static_cast<float*>(dh2));
-      break;
-    case MAAI_DT_BF16:
-      e = launch_k(maai::dh_kernel<__nv_bfloat16>, dim3(grid), dim3(wpb * 32), 0, s, dz_acc, dz_extra,
-                   static_cast<const __nv_bfloat16*>(h1), static_cast<const __nv_bfloat16*>(h2), inv_norm, grad_loss,
-                   rowsum_l, pos_cos, b, d, d_pad, inv_tau, key_grad, need_mask, static_cast<__nv_bfloat16*>(dh1),
-                   static_cast<__nv_bfloat16*>(dh2));
-      break;
-    case MAAI_DT_F16:
-      e = launch_k(maai::dh_kernel<__half>, dim3(grid), dim3(wpb * 32), 0, s, dz_acc, dz_extra,
-                   static_cast<const __half*>(h1), static_cast<const __half*>(h2), inv_norm, grad_loss, rowsum_l,
-                   pos_cos, b, d, d_pad, inv_tau, key_grad, need_mask, static_cast<__half*>(dh1),
-                   static_cast<__half*>(dh2));
-      break;
-    default:
-      return fail(MAAI_E_ARG, "in_dtype must be MAAI_DT_F32, MAAI_DT_BF16 or MAAI_DT_F16");
+  const size_t esz = in_dtype == MAAI_DT_F32 ? 4 : 2;
+  const int vec = d_pad / 32;
+  auto al = [&](const void* p) { return !p || (reinterpret_cast<uintptr_t>(p) % (vec * esz)) == 0; };
+  const bool vec_ok = (d % vec) == 0 && al(h1) && al(h2) && al(dh1) && al(dh2);
+  cudaError_t e = cudaSuccess;
+#define MAAI_K4(T, V)                                                                                       \
+  e = launch_k(maai::dh_kernel<T, V>, dim3(grid), dim3(wpb * 32), 0, s, dz_acc, dz_extra,                   \
+               static_cast<const T*>(h1), static_cast<const T*>(h2), inv_norm, grad_loss, rowsum_l, pos_cos, \
+               b, d, vec_ok, inv_tau, key_grad, need_mask, static_cast<T*>(dh1), static_cast<T*>(dh2))
+#define MAAI_K4_DP(T)               \
+  switch (d_pad) {                  \
+    case 64: MAAI_K4(T, 2); break;  \
+    case 128: MAAI_K4(T, 4); break; \
+    default: MAAI_K4(T, 8); break;  \
   }
+  switch (in_dtype) {
+    case MAAI_DT_F32: MAAI_K4_DP(float); break;
+    case MAAI_DT_BF16: MAAI_K4_DP(__nv_bfloat16); break;
+    case MAAI_DT_F16: MAAI_K4_DP(__half); break;
+    default: return fail(MAAI_E_ARG, "in_dtype must be MAAI_DT_F32, MAAI_DT_BF16 or MAAI_DT_F16");
+  }
+#undef MAAI_K4_DP
+#undef MAAI_K4
   MAAI_CUDA(e);
   return MAAI_OK;
 }
@@ -594,7 +650,8 @@ static int bwd_check(int b, int world, int rank, int d, int d_pad, int need_mask
 int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, int key_grad,
                     const float* rowsum_l, const float* pos_cos, const void* h1, const void* h2, int in_dtype,
                     const float* inv_norm, const float* grad_loss, int b, int world, int rank, int d, int d_pad,
-                    float inv_tau, int need_mask, void* dh1, void* dh2, float* dz_acc, void* stream) {
+                    float inv_tau, int need_mask, void* dh1, void* dh2, float* dz_acc, int flags, void* stream) {
+  if (flags & ~MAAI_F_PREZEROED) return fail(MAAI_E_ARG, "unknown flag");
   if (!z_glob || !r_row || !r_col || !rowsum_l || !pos_cos || !h1 || !h2 || !inv_norm || !grad_loss || !dz_acc)
     return fail(MAAI_E_ARG, "null pointer");
   int rc = bwd_check(b, world, rank, d, d_pad, need_mask);
@@ -604,7 +661,8 @@ int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, 
   if (!aligned16(z_glob) || !aligned16(r_col) || !aligned16(dz_acc))
     return fail(MAAI_E_ARG, "z_glob, r_col and dz_acc must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if ((rc = bwd_tiles_impl(z_glob, r_row, r_col, b, world, rank, d_pad, inv_tau, need_mask, dz_acc, s)) != MAAI_OK)
+  if ((rc = bwd_tiles_impl(z_glob, r_row, r_col, b, world, rank, d_pad, inv_tau, need_mask, dz_acc, s,
+                           flags & MAAI_F_PREZEROED)) != MAAI_OK)
     return rc;
   return bwd_dh_impl(dz_acc, nullptr, rowsum_l, pos_cos, h1, h2, in_dtype, inv_norm, grad_loss, b, d, d_pad,
                      inv_tau, key_grad, need_mask, dh1, dh2, s);

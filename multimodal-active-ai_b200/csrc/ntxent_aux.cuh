@@ -31,49 +31,39 @@ __device__ __forceinline__ float warp_sum(float v) {
 constexpr float kNormEps = 1e-12f;  // F.normalize default eps (Objective.py:42-43)
 constexpr int kMaxPerLane = 8;      // d <= 256 -> at most 8 elements per lane
 
-// One warp per pair k: rows k (view a) and b + k (view b) of the rank-local z block.
-// z_out: (2b, DP) bf16, columns [d, DP) zero-filled so the padded tile MMA sees exact zeros.
-template <typename T>
-__global__ void __launch_bounds__(256)
-normalize_cast_kernel(const T* __restrict__ h1, const T* __restrict__ h2, int b, int d, int dp,
-                      __nv_bfloat16* __restrict__ z_out, float* __restrict__ inv_norm,
-                      float* __restrict__ pos_cos) {
-  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  pdl_launch_dependents<1>();
-  pdl_wait();
-  if (k >= b) return;
-  float a[kMaxPerLane], c[kMaxPerLane];
-  float sa = 0.f, sc = 0.f;
+// VEC consecutive elements of a row as ONE aligned vector load (4/8/16/32 bytes) when the caller has
+// checked alignment (d % VEC == 0 and an aligned base), else element by element with a bound check.
+template <typename T, int VEC>
+__device__ __forceinline__ void load_row_chunk(const T* __restrict__ row, int e0, int d, bool vec_ok, float (&out)[VEC]) {
+  struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
+  if (vec_ok) {  // d % VEC == 0: a chunk lies entirely inside or entirely outside the row
+    if (e0 < d) {
+      const Pack pk = *reinterpret_cast<const Pack*>(row + e0);
 #pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) {
-    const int e = lane + 32 * i;
-    a[i] = (e < d) ? to_f32<T>(h1[(size_t)k * d + e]) : 0.f;
-    c[i] = (e < d) ? to_f32<T>(h2[(size_t)k * d + e]) : 0.f;
-    sa += a[i] * a[i];
-    sc += c[i] * c[i];
-  }
-  sa = warp_sum(sa);
-  sc = warp_sum(sc);
-  const float ia = 1.f / fmaxf(sqrtf(sa), kNormEps);
-  const float ic = 1.f / fmaxf(sqrtf(sc), kNormEps);
-  float dot = 0.f;
+      for (int i = 0; i < VEC; ++i) out[i] = to_f32<T>(pk.v[i]);
+    } else {
 #pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) {
-    const int e = lane + 32 * i;
-    if (e < dp) {
-      const __nv_bfloat16 za = __float2bfloat16_rn(a[i] * ia);
-      const __nv_bfloat16 zc = __float2bfloat16_rn(c[i] * ic);
-      z_out[(size_t)k * dp + e] = za;
-      z_out[(size_t)(b + k) * dp + e] = zc;
-      dot += __bfloat162float(za) * __bfloat162float(zc);  // same bf16 values the MMA multiplies
+      for (int i = 0; i < VEC; ++i) out[i] = 0.f;
     }
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) out[i] = (e0 + i < d) ? to_f32<T>(row[e0 + i]) : 0.f;
   }
-  dot = warp_sum(dot);
-  if (lane == 0) {
-    inv_norm[k] = ia;
-    inv_norm[b + k] = ic;
-    pos_cos[k] = dot;
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void store_row_chunk(T* __restrict__ row, int e0, int d, bool vec_ok, const float (&v)[VEC]) {
+  struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
+  if (vec_ok) {
+    if (e0 < d) {
+      Pack pk;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) pk.v[i] = from_f32<T>(v[i]);
+      *reinterpret_cast<Pack*>(row + e0) = pk;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+      if (e0 + i < d) row[e0 + i] = from_f32<T>(v[i]);
   }
 }
 
@@ -93,30 +83,41 @@ __device__ __forceinline__ void multimem_st_f32(float* a, float v) {
   asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(a), "f"(v) : "memory");
 }
 
-// K1 fused with the embedding all-gather (Objective.py:41-43 + :52-53, 102-114): the normalised bf16
-// rows are stored straight into slot `rank` of EVERY rank's (world, 2b, DP) key buffer through
-// peer-mapped (NVLink) pointers, so no collective kernel runs and the payload crosses the switch
-// while the rows are being produced; a symmetric-memory barrier then orders the stores before any
-// rank's tile kernel reads its buffer.  One warp per pair; a lane owns DP/32 consecutive elements
-// of both rows, so every store is a 4/8/16-byte vector and a warp writes whole 128..512-B rows.
+// K1: F.normalize of both views (Objective.py:41-43) -> bf16 rows, 1/norm, positive cosine; one warp per
+// pair k (rows k and b + k of the rank's stacked block); a lane owns DP/32 = VEC consecutive elements of
+// both rows, so the input loads and the bf16 stores are 4..32-byte vectors and a warp moves whole rows.
+// Destinations of the bf16 rows (any combination):
+//   z_local    this rank's (2b, DP) block (single rank, or the NCCL all-gather's send slot)
+//   mc_base    NVSwitch multicast mapping of every rank's (world, 2b, DP) key buffer: ONE multimem.st per
+//              chunk, replicated by the switch                         } the cross-replica gather of
+//   peer_base  table of `world` peer-mapped key buffers: unicast stores } Objective.py:52-53, 102-114 fused
+// Columns [d, DP) are zero so the padded tile MMA sees exact zeros.
+// The kernel also zero-fills `zero_words` 32-bit words at zero_fill (the step's accumulators: row sums,
+// CTA-done counter, dz accumulator), which removes the separate memset / zero kernels of the step.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
-normalize_cast_peer_kernel(const T* __restrict__ h1, const T* __restrict__ h2, int b, int d,
-                           const unsigned long long* __restrict__ peer_base, unsigned long long mc_base,
-                           int world, int rank, float* __restrict__ inv_norm, float* __restrict__ pos_cos) {
+normalize_cast_kernel(const T* __restrict__ h1, const T* __restrict__ h2, int b, int d, bool vec_ok,
+                      __nv_bfloat16* __restrict__ z_local, const unsigned long long* __restrict__ peer_base,
+                      unsigned long long mc_base, int world, int rank, float* __restrict__ inv_norm,
+                      float* __restrict__ pos_cos, uint32_t* __restrict__ zero_fill, size_t zero_words) {
   constexpr int DP = VEC * 32;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   pdl_launch_dependents<1>();
   pdl_wait();
+  if (zero_words) {  // grid-strided 16-byte stores (zero_fill is 16-byte aligned, checked by the host)
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    uint4* p4 = reinterpret_cast<uint4*>(zero_fill);
+    for (size_t i = tid; i < zero_words / 4; i += nth) p4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (size_t i = (zero_words / 4) * 4 + tid; i < zero_words; i += nth) zero_fill[i] = 0u;
+  }
   if (k >= b) return;
   float a[VEC], c[VEC];
+  load_row_chunk<T, VEC>(h1 + (size_t)k * d, lane * VEC, d, vec_ok, a);
+  load_row_chunk<T, VEC>(h2 + (size_t)k * d, lane * VEC, d, vec_ok, c);
   float sa = 0.f, sc = 0.f;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    const int e = lane * VEC + i;
-    a[i] = (e < d) ? to_f32<T>(h1[(size_t)k * d + e]) : 0.f;
-    c[i] = (e < d) ? to_f32<T>(h2[(size_t)k * d + e]) : 0.f;
     sa += a[i] * a[i];
     sc += c[i] * c[i];
   }
@@ -135,14 +136,16 @@ normalize_cast_peer_kernel(const T* __restrict__ h1, const T* __restrict__ h2, i
   dot = warp_sum(dot);
   using Vec = typename std::conditional<VEC == 2, uint32_t, typename std::conditional<VEC == 4, uint2, uint4>::type>::type;
   const Vec va = *reinterpret_cast<const Vec*>(za), vc = *reinterpret_cast<const Vec*>(zc);
+  if (z_local) {
+    *reinterpret_cast<Vec*>(z_local + (size_t)k * DP + lane * VEC) = va;
+    *reinterpret_cast<Vec*>(z_local + (size_t)(b + k) * DP + lane * VEC) = vc;
+  }
   const size_t off_a = (((size_t)rank * 2 * b + k) * DP + lane * VEC) * sizeof(__nv_bfloat16);
   const size_t off_c = (((size_t)rank * 2 * b + b + k) * DP + lane * VEC) * sizeof(__nv_bfloat16);
   if (mc_base) {
-    // NVSwitch multicast mapping of the same buffers: ONE store, replicated into every rank's copy by
-    // the switch (multimem.st), instead of `world` unicast stores
     multimem_st(reinterpret_cast<char*>(mc_base) + off_a, va);
     multimem_st(reinterpret_cast<char*>(mc_base) + off_c, vc);
-  } else {
+  } else if (peer_base) {
     for (int p = 0; p < world; ++p) {
       char* base = reinterpret_cast<char*>(peer_base[p]);
       *reinterpret_cast<Vec*>(base + off_a) = va;
@@ -156,21 +159,79 @@ normalize_cast_peer_kernel(const T* __restrict__ h1, const T* __restrict__ h2, i
   }
 }
 
-// One thread-block cluster of 8 CTAs (8192 threads), deterministic: fixed thread-strided partial
-// sums in fp64, one value per CTA written into CTA 0's shared memory over DSMEM, summed in rank
-// order.  (A single 1024-thread block took 45 us at 65536 rows, 1.7 % of the step.)
-// With e_pos = exp((cos_pos - 1)/tau) and l' = sum over negatives:
+// Per-row tail of the forward (Objective.py:76-79): with e_pos = exp((cos_pos - 1)/tau) and l' = sum over
+// the negatives,
 //   lse_i - s_i,pos = ln(e_pos + l'_i) - ln(e_pos) = log1p(l'_i / e_pos)      (Objective.py:76-77)
 //   loss = (1/b) * sum_{i < 2b} log1p(l'_i / e_pos(i))                          (Objective.py:79)
-// and r_i = 1 / (b * (e_pos + l'_i)) for the backward.  r_out may be null.  peer_r (optional): device
-// array of `world` peer-mapped base addresses of every rank's gathered r array.  stage_tab (optional):
-// `world` peer-mapped base addresses of every rank's (world, 2b) staging vectors (maai_ntxent_fwd_sym).
+// and r_i = 1 / (b * (e_pos + l'_i)) for the backward.  Thread `tid` of `nth` takes rows tid, tid + nth, ...
+// and returns its partial sum (fp64, fixed order: the reductions built on it are deterministic given l).
+// r_out may be null.  peer_r (optional): device array of `world` peer-mapped base addresses of every
+// rank's gathered r array; mc_r: multicast address of the same.  stage_tab (optional): `world` peer-mapped
+// base addresses of every rank's (world, 2b) staging vectors (maai_ntxent_fwd_sym).
+struct FinalizeArgs {
+  float* l;
+  const float* pos_cos;
+  int b;
+  float inv_tau;
+  float* r_out;
+  float* loss_out;
+  const unsigned long long* peer_r;
+  int world;
+  int my_rank;
+  float* mc_r;
+  const unsigned long long* stage_tab;
+};
+__device__ __forceinline__ double finalize_rows(const FinalizeArgs& f, int tid, int nth) {
+  double acc = 0.0;
+  const float inv_b = 1.f / float(f.b);
+  const float c1 = f.inv_tau * 1.4426950408889634f;
+  for (int i = tid; i < 2 * f.b; i += nth) {
+    float ln = __ldcg(f.l + i);  // written by other CTAs' atomics: read at L2
+    if (f.stage_tab) {
+      // symmetric forward across ranks: the other ranks hold partial row sums of this rank's anchors
+      // (the tiles they computed for their own column sums) in slot my_rank of their staging vectors;
+      // read them over NVLink (uncached: written by the peers' kernels before the barrier)
+      for (int p = 0; p < f.world; ++p)
+        if (p != f.my_rank)
+          ln += __ldcv(reinterpret_cast<const float*>(f.stage_tab[p]) + (size_t)f.my_rank * 2 * f.b + i);
+      f.l[i] = ln;  // the backward's positive-pair term needs the complete row sum
+    }
+    const float ep = ex2_approx(fmaf(__ldg(f.pos_cos + (i < f.b ? i : i - f.b)), c1, -c1));
+    acc += double(log1pf(ln / ep));
+    const float r = inv_b / (ep + ln);
+    if (f.r_out) f.r_out[i] = r;
+    // fused all-gather of the row factors: slot `rank` of every rank's r array (NVLink stores)
+    if (f.mc_r) {
+      multimem_st_f32(f.mc_r + (size_t)f.my_rank * 2 * f.b + i, r);
+    } else if (f.peer_r) {
+      for (int p = 0; p < f.world; ++p) reinterpret_cast<float*>(f.peer_r[p])[(size_t)f.my_rank * 2 * f.b + i] = r;
+    }
+  }
+  return acc;
+}
+// Sum of the per-thread partials of one CTA, in a fixed order (warp shuffle tree, then warp 0 over the
+// per-warp values).  `part` = shared scratch of >= 32 doubles.  Valid in thread 0.
+__device__ __forceinline__ double finalize_block_sum(double acc, double* part) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  double v = 0.0;
+  if (threadIdx.x < 32) {
+    v = (threadIdx.x < ((blockDim.x + 31) >> 5)) ? part[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  }
+  return v;
+}
+
+// Stand-alone finalize: one thread-block cluster of 8 CTAs (8192 threads), one value per CTA written into
+// CTA 0's shared memory over DSMEM, summed in rank order.  (A single 1024-thread block took 45 us at 65536
+// rows.)  Used for large batches and after the barrier of the cross-rank symmetric forward; small and
+// medium batches finalize in the tail of the tile kernel itself (last CTA done, ntxent_tile.cuh).
 constexpr int kFinalizeCluster = 8;
 __global__ void __cluster_dims__(kFinalizeCluster, 1, 1) __launch_bounds__(1024)
-finalize_loss_kernel(float* __restrict__ l, const float* __restrict__ pos_cos, int b,
-                     float inv_tau, float* __restrict__ r_out, float* __restrict__ loss_out,
-                     const unsigned long long* __restrict__ peer_r = nullptr, int world = 1, int my_rank = 0,
-                     float* mc_r = nullptr, const unsigned long long* __restrict__ stage_tab = nullptr) {
+finalize_loss_kernel(const __grid_constant__ FinalizeArgs f) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ double part[32];
@@ -178,46 +239,15 @@ finalize_loss_kernel(float* __restrict__ l, const float* __restrict__ pos_cos, i
   const unsigned rank = cluster.block_rank();
   pdl_launch_dependents<8>();
   pdl_wait();
-  double acc = 0.0;
-  const float inv_b = 1.f / float(b);
-  const float c1 = inv_tau * 1.4426950408889634f;
-  for (int i = rank * blockDim.x + threadIdx.x; i < 2 * b; i += kFinalizeCluster * blockDim.x) {
-    float ln = l[i];
-    if (stage_tab) {
-      // symmetric forward across ranks: the other ranks hold partial row sums of this rank's anchors
-      // (the tiles they computed for their own column sums) in slot my_rank of their staging vectors;
-      // read them over NVLink (uncached: written by the peers' kernels before the barrier)
-      for (int p = 0; p < world; ++p)
-        if (p != my_rank) ln += __ldcv(reinterpret_cast<const float*>(stage_tab[p]) + (size_t)my_rank * 2 * b + i);
-      l[i] = ln;  // the backward's positive-pair term needs the complete row sum
-    }
-    const float ep = ex2_approx(fmaf(pos_cos[i < b ? i : i - b], c1, -c1));
-    acc += double(log1pf(ln / ep));
-    const float r = inv_b / (ep + ln);
-    if (r_out) r_out[i] = r;
-    // fused all-gather of the row factors: slot `rank` of every rank's r array (NVLink stores)
-    if (mc_r) {
-      multimem_st_f32(mc_r + (size_t)my_rank * 2 * b + i, r);
-    } else if (peer_r) {
-      for (int p = 0; p < world; ++p) reinterpret_cast<float*>(peer_r[p])[(size_t)my_rank * 2 * b + i] = r;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double v = (threadIdx.x < (blockDim.x >> 5)) ? part[threadIdx.x] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0) cluster.map_shared_rank(cta_part, 0)[rank] = v;
-  }
+  const double acc = finalize_rows(f, rank * blockDim.x + threadIdx.x, kFinalizeCluster * blockDim.x);
+  const double v = finalize_block_sum(acc, part);
+  if (threadIdx.x == 0) cluster.map_shared_rank(cta_part, 0)[rank] = v;
   cluster.sync();
   if (rank == 0 && threadIdx.x == 0) {
-    double v = 0.0;
+    double t = 0.0;
 #pragma unroll
-    for (int r = 0; r < kFinalizeCluster; ++r) v += cta_part[r];
-    *loss_out = float(v * double(inv_b));
+    for (int r = 0; r < kFinalizeCluster; ++r) t += cta_part[r];
+    *f.loss_out = float(t / double(f.b));
   }
 }
 
@@ -235,20 +265,22 @@ __global__ void __launch_bounds__(256) zero_kernel(uint32_t* __restrict__ p, siz
   }
 }
 
-// One warp per anchor row i of the views that need a gradient.
+// One warp per anchor row i of the views that need a gradient; a lane owns VEC = dp/32 consecutive
+// elements (vector loads of h and of the fp32 accumulator, vector stores of dh).
 //   dz_i = (g / tau) * (A_i + cpos_i z_pos(i)),  A = dz_acc (+ dz_extra) (fp32, stride dp, positive column excluded)
 //   cpos_i = [e_pos/(e_pos + l'_i) - 1]/b  (+ the same with l'_pos when the key side is kept)
 //          = -(1/b) [ l'_i/(e_pos + l'_i) + key_grad * l'_pos/(e_pos + l'_pos) ]
 // i.e. the positive pair's softmax-minus-target coefficient without any cancellation.
 //   dh_i = inv_i * (dz_i - z_i (z_i . dz_i))       (rows with ||h|| < eps: dh = dz * inv)
 // z_i, z_pos are recomputed in fp32 from h (not the bf16 copies).
-template <typename T>
+template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 dh_kernel(const float* __restrict__ dz_acc, const float* __restrict__ dz_extra, const T* __restrict__ h1,
           const T* __restrict__ h2,
           const float* __restrict__ inv_norm, const float* __restrict__ grad_loss,
-          const float* __restrict__ lneg, const float* __restrict__ pos_cos, int b, int d, int dp,
+          const float* __restrict__ lneg, const float* __restrict__ pos_cos, int b, int d, bool vec_ok,
           float inv_tau, int key_grad, int need_mask, T* __restrict__ dh1, T* __restrict__ dh2) {
+  constexpr int DP = VEC * 32;
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   pdl_launch_dependents<16>();
@@ -268,33 +300,44 @@ dh_kernel(const float* __restrict__ dz_acc, const float* __restrict__ dz_extra, 
   const int ip = view ? k : b + k;  // local row of the positive
   const float c1 = inv_tau * 1.4426950408889634f;
   const float e_pos = ex2_approx(fmaf(pos_cos[k], c1, -c1));
-  const float li = lneg[i], lp = lneg[ip];
+  const float li = __ldcg(lneg + i), lp = __ldcg(lneg + ip);
   const float cpos = -(li / (e_pos + li) + (key_grad ? lp / (e_pos + lp) : 0.f)) / float(b);
-  float z[kMaxPerLane], dz[kMaxPerLane];
+  const int e0 = lane * VEC;
+  float z[VEC], zp[VEC], a[VEC], dz[VEC];
+  load_row_chunk<T, VEC>(hi, e0, d, vec_ok, z);
+  load_row_chunk<T, VEC>(hp, e0, d, vec_ok, zp);
+  // the accumulator rows are DP wide and 16-byte aligned: always vector loads (L2: written by atomics)
+  {
+    const float* src = dz_acc + (size_t)i * DP + e0;
+#pragma unroll
+    for (int j = 0; j < VEC; j += 2) {
+      const float2 t = __ldcg(reinterpret_cast<const float2*>(src + j));
+      a[j] = t.x;
+      a[j + 1] = t.y;
+    }
+    if (dz_extra) {  // key-side sums that arrived by reduce-scatter
+      const float* ex = dz_extra + (size_t)i * DP + e0;
+#pragma unroll
+      for (int j = 0; j < VEC; j += 2) {
+        const float2 t = __ldcg(reinterpret_cast<const float2*>(ex + j));
+        a[j] += t.x;
+        a[j + 1] += t.y;
+      }
+    }
+  }
   float dot = 0.f;
 #pragma unroll
-  for (int j = 0; j < kMaxPerLane; ++j) {
-    const int e = lane + 32 * j;
-    if (e < d) {
-      z[j] = to_f32<T>(hi[e]) * inv_i;
-      const float zp = to_f32<T>(hp[e]) * inv_p;
-      float a = dz_acc[(size_t)i * dp + e];
-      if (dz_extra) a += dz_extra[(size_t)i * dp + e];  // key-side sums that arrived by reduce-scatter
-      dz[j] = gs * (a + cpos * zp);
-      dot += z[j] * dz[j];
-    } else {
-      z[j] = 0.f;
-      dz[j] = 0.f;
-    }
+  for (int j = 0; j < VEC; ++j) {
+    z[j] *= inv_i;
+    dz[j] = (e0 + j < d) ? gs * (a[j] + cpos * (zp[j] * inv_p)) : 0.f;
+    dot += z[j] * dz[j];
   }
   dot = warp_sum(dot);
   const bool clamped = inv_i >= 1.f / kNormEps;  // ||h|| < eps: z = h/eps, plain scaling
-  T* out = (view ? dh2 : dh1) + (size_t)k * d;
+  float out[VEC];
 #pragma unroll
-  for (int j = 0; j < kMaxPerLane; ++j) {
-    const int e = lane + 32 * j;
-    if (e < d) out[e] = from_f32<T>(inv_i * (clamped ? dz[j] : (dz[j] - z[j] * dot)));
-  }
+  for (int j = 0; j < VEC; ++j) out[j] = inv_i * (clamped ? dz[j] : (dz[j] - z[j] * dot));
+  store_row_chunk<T, VEC>((view ? dh2 : dh1) + (size_t)k * d, e0, d, vec_ok, out);
 }
 
 }  // namespace maai

@@ -40,6 +40,7 @@
 #pragma once
 #include <type_traits>
 
+#include "ntxent_aux.cuh"
 #include "ptx_sm100.cuh"
 
 // Of every 8 column pairs a softmax thread handles, this many take the polynomial exp2 on the FMA
@@ -165,6 +166,11 @@ struct TileParams {
   int g_nkt[kMaxGroups];
   long long g_items[kMaxGroups];  // items of the group (row blocks x key tiles; group 0 triangular)
   float* g_out[kMaxGroups];
+  // FWD, optional: the last CTA to finish runs the per-row tail of the forward (loss, row factors and
+  // their peer stores: finalize_rows of ntxent_aux.cuh) instead of a separate finalize launch.
+  // done_ctr: zero-initialised 32-bit counter (K1's zero fill); null = no in-kernel finalize.
+  unsigned int* done_ctr;
+  FinalizeArgs fin;
 };
 
 template <int D, bool BWD, int NQ>
@@ -391,6 +397,22 @@ struct GrpWalk {
   }
 };
 
+// Forward, last CTA done: every other CTA's sums are in L2 (their threads fenced before the CTA took its
+// ticket), so this CTA runs the per-row tail (finalize_rows) over all 2b rows.  Out of line on purpose: it
+// runs once per launch and must not cost the hot loops a register.  flag_smem / part_smem: shared-window
+// addresses of dead regions (the mbarriers, the Q tiles).
+__device__ __noinline__ void fwd_tail_finalize(const TileParams& p, uint32_t flag_smem, uint32_t part_smem) {
+  uint32_t* flag = static_cast<uint32_t*>(__cvta_shared_to_generic(flag_smem));
+  if (threadIdx.x == 0) *flag = (atomicAdd(p.done_ctr, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (*flag) {
+    __threadfence();
+    double* part = static_cast<double*>(__cvta_shared_to_generic(part_smem));
+    const double v = finalize_block_sum(finalize_rows(p.fin, threadIdx.x, blockDim.x), part);
+    if (threadIdx.x == 0) *p.fin.loss_out = float(v / double(p.fin.b));
+  }
+}
+
 template <int D, bool BWD, int NQ, bool RANK = false, bool SYM = false, bool GRP = false>
 __global__ void __launch_bounds__(640, 1)
 ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
@@ -461,6 +483,13 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
+  // prefetch) touches no global data and may overlap the tail of the previous kernel; from here on
+  // every role reads what earlier kernels wrote (z rows, r factors, zeroed accumulators) or adds to
+  // it, so EVERY thread waits for the previous grid -- also the threads that never touch global
+  // memory: a grid whose threads skip the wait can complete before its predecessor has, and the
+  // kernel after it would then see that predecessor's writes unordered (round 1's PDL failure).
+  pdl_wait();
   if (C::REGS_SM > 96) {
     if (warp < C::SM_WARP0) reg_dealloc<C::REGS_WG0>();
     else reg_alloc<C::REGS_SM>();
@@ -1037,9 +1066,11 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
 #endif
   }
 
+  if (!BWD && !GRP && p.done_ctr) __threadfence();  // this thread's row / column sums before the CTA's ticket
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (!BWD && !GRP && p.done_ctr) fwd_tail_finalize(p, smem_base + C::OFF_BAR, smem_base + C::OFF_Q);
 }
 
 }  // namespace maai

@@ -228,3 +228,114 @@ def positive_rank_oracle(h1_ranks, h2_ranks, hidden_norm=True):
         out.append((ab > pos[:, None]).sum(axis=1).astype(np.int64))
         off += b
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Sampled-anchor oracle for BASELINE.json's full sizes (32768 / 65536 pairs): the full fp64 oracle
+# above is O(B^2 d) in time AND needs every row; here only `pairs` sampled pairs of one rank are
+# evaluated against ALL 2B keys, in fp64, row-blocked.
+# ------------------------------------------------------------------------------------------------
+def row_denominators(H1, H2, temperature, rows=None, block=1024):
+    """den_i = sum_{j != i} exp((z_i.z_j - 1)/tau) over ALL 2B keys (the self-similarity entry is the
+    one Objective.py:68,71 masks with -1e9; the positive is included), for the stacked global rows
+    [view a of every pair; view b of every pair] -- i.e. exp(-1/tau) times the softmax denominator of
+    Objective.py:76-77, 123-125 (logits cat([cross, self], 1)).  ``rows``: indices into the stacked
+    2B rows (default: all, O(B^2 d) -- for small B and for validating faster all-row references).
+    fp64 numpy.  Returns (len(rows),)."""
+    z1, _ = l2_normalise(H1)
+    z2, _ = l2_normalise(H2)
+    Z = np.concatenate([z1, z2], 0)
+    rows = np.arange(Z.shape[0]) if rows is None else np.asarray(rows, np.int64)
+    out = np.empty(len(rows))
+    for r0 in range(0, len(rows), block):
+        idx = rows[r0:r0 + block]
+        e = np.exp((Z[idx] @ Z.T - 1.0) / float(temperature))
+        e[np.arange(len(idx)), idx] = 0.0
+        out[r0:r0 + block] = e.sum(1)
+    return out
+
+
+def ntxent_rows_oracle(H1, H2, pairs, temperature, rank=0, world=1, den_all=None, key_grad=True, block=256):
+    """Loss terms and input gradients of SAMPLED anchors of one rank against all 2B global keys.
+
+    H1, H2   (B, d) the GLOBAL batch in rank order (rank p owns pairs [p*b, (p+1)*b), b = B/world:
+             Objective.py:52-53 torch.cat(tensor_list, 0)).
+    pairs    indices k in [0, b) of the sampled pairs of rank ``rank``; both anchors of a pair are
+             evaluated (view a = hidden1[k], view b = hidden2[k]).
+    den_all  (2B,) ``row_denominators`` of every stacked global row.  Only the key-side gradient
+             needs it (row j's softmax normaliser for every key j); if None it is computed here in
+             fp64 (O(B^2 d)).  Tests at B >= 16384 pass a faster all-row reference that they first
+             validate against this module's fp64 values on the sampled rows.
+    key_grad True: gradient of sum_ranks loss_rank (single-process reference on the concatenated batch
+             after DDP's 1/W; Objective.py:60-61 aliasing keys and queries); False: the reference's own
+             world_size > 1 gradient, keys detached by the non-differentiable all_gather
+             (Objective.py:112-114).
+
+    Returns dict:
+      terms   (2, n)  lse_i - s_i,pos per sampled anchor (view a, view b): the summands of
+                      Objective.py:123-125 before the division by b
+      lneg    (2, n)  sum over the NEGATIVES of exp((z_i.z_j - 1)/tau) (no self, no positive)
+      den     (2, n)  the same plus the positive (the sampled entries of ``row_denominators``)
+      pos_cos (n,)    cosine of the pair
+      dh1, dh2 (n, d) gradient rows of hidden1[pairs], hidden2[pairs] (rank-local indexing)
+    """
+    H1 = np.asarray(H1, np.float64)
+    H2 = np.asarray(H2, np.float64)
+    tau = float(temperature)
+    B, d = H1.shape
+    assert B % world == 0
+    b = B // world
+    pairs = np.asarray(pairs, np.int64)
+    n = len(pairs)
+    gk = rank * b + pairs                       # global pair index (labels_idx + rank*b, Objective.py:55)
+    z1, n1 = l2_normalise(H1)
+    z2, n2 = l2_normalise(H2)
+    Z = np.concatenate([z1, z2], 0)             # stacked global rows: view a, then view b
+    if den_all is None and key_grad:
+        den_all = row_denominators(H1, H2, tau)
+    out = dict(terms=np.empty((2, n)), lneg=np.empty((2, n)), den=np.empty((2, n)),
+               pos_cos=(z1[gk] * z2[gk]).sum(1))
+    dz = [np.empty((n, d)), np.empty((n, d))]
+    inv_den_all = None if den_all is None else 1.0 / np.asarray(den_all, np.float64)
+    for v in (0, 1):
+        own = gk + v * B                        # stacked row index of the anchors
+        pos = gk + (1 - v) * B                  # ... of their positives
+        for r0 in range(0, n, block):
+            sl = slice(r0, min(n, r0 + block))
+            m = sl.stop - sl.start
+            ar = np.arange(m)
+            q = Z[own[sl]]
+            e = np.exp((q @ Z.T - 1.0) / tau)   # (m, 2B)
+            e[ar, own[sl]] = 0.0                # self-similarity mask (Objective.py:68,71)
+            den = e.sum(1)
+            e_pos = e[ar, pos[sl]].copy()
+            out["den"][v, sl] = den
+            out["lneg"][v, sl] = den - e_pos
+            out["terms"][v, sl] = np.log(den) - np.log(e_pos)
+            # G_ij = softmax_ij - onehot_ij (divided by the local b below, Objective.py:125)
+            w = e / den[:, None]
+            if key_grad:                        # + G_ji = E_ij / den_j - [i == pos(j)]
+                w += e * inv_den_all[None, :]
+                w[ar, pos[sl]] -= 2.0
+            else:
+                w[ar, pos[sl]] -= 1.0
+            dz[v][sl] = (w @ Z) / (b * tau)
+    out["dh1"] = _normalise_backward(H1[gk], z1[gk], n1[gk], dz[0])
+    out["dh2"] = _normalise_backward(H2[gk], z2[gk], n2[gk], dz[1])
+    return out
+
+
+def loss_from_denominators(H1, H2, den_all, temperature, rank=0, world=1):
+    """Per-rank loss of Objective.py:76-79 from the all-row denominators:
+    (1/b) sum over the rank's 2b anchors of [ln den_i + 1/tau - cos_i,pos / tau]."""
+    H1 = np.asarray(H1, np.float64)
+    H2 = np.asarray(H2, np.float64)
+    B = H1.shape[0]
+    b = B // world
+    z1, _ = l2_normalise(H1[rank * b:(rank + 1) * b])
+    z2, _ = l2_normalise(H2[rank * b:(rank + 1) * b])
+    cos = (z1 * z2).sum(1)
+    den = np.asarray(den_all, np.float64)
+    idx = np.arange(rank * b, (rank + 1) * b)
+    t = float(temperature)
+    return float((np.log(den[idx]) + np.log(den[B + idx]) + 2.0 * (1.0 - cos) / t).sum() / b)

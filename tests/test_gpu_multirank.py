@@ -40,14 +40,14 @@ def test_emulated_ranks_one_gpu(world, b, d, tau):
     dh = [(h1r[p].to(dev), h2r[p].to(dev)) for p in range(world)]
     for p in range(world):
         _lib.check(lib.maai_ntxent_normalize(dh[p][0].data_ptr(), dh[p][1].data_ptr(), b, d, 0,
-                                             z_all[p].data_ptr(), inv[p].data_ptr(), cos[p].data_ptr(), s), "k1")
+                                             z_all[p].data_ptr(), inv[p].data_ptr(), cos[p].data_ptr(), None, 0, s), "k1")
     rowsum = torch.zeros(world, 2 * b, device=dev)
     r_col = torch.zeros(lib.maai_ntxent_r_len(b, world), device=dev)
     losses = torch.zeros(world, device=dev)
     for p in range(world):
         _lib.check(lib.maai_ntxent_fwd(z_all.data_ptr(), b, world, p, dp, 1.0 / tau, cos[p].data_ptr(),
                                        rowsum[p].data_ptr(), r_col[p * 2 * b:].data_ptr(),
-                                       losses[p:].data_ptr(), s), "k2")
+                                       losses[p:].data_ptr(), 0, s), "k2")
     ol, o1q, o2q = O.contrastive_loss_oracle_distributed([h.numpy() for h in h1r], [h.numpy() for h in h2r], tau, key_grad=False)
     _, o1f, o2f = O.contrastive_loss_oracle_distributed([h.numpy() for h in h1r], [h.numpy() for h in h2r], tau, key_grad=True)
     got = losses.cpu().numpy()
@@ -64,7 +64,7 @@ def test_emulated_ranks_one_gpu(world, b, d, tau):
                                            (r_col if key_grad else zeros).data_ptr(), key_grad,
                                            rowsum[p].data_ptr(), cos[p].data_ptr(), dh[p][0].data_ptr(),
                                            dh[p][1].data_ptr(), 0, inv[p].data_ptr(), one.data_ptr(), b, world, p,
-                                           d, dp, 1.0 / tau, 3, g1.data_ptr(), g2.data_ptr(), acc.data_ptr(), s), "k3")
+                                           d, dp, 1.0 / tau, 3, g1.data_ptr(), g2.data_ptr(), acc.data_ptr(), 0, s), "k3")
             torch.cuda.synchronize()
             assert rel_fro(g1.cpu().numpy(), r1[p]) <= 1e-2, (p, key_grad)
             assert rel_fro(g2.cpu().numpy(), r2[p]) <= 1e-2, (p, key_grad)
@@ -91,7 +91,7 @@ def test_emulated_ranks_fused_topk(world, b, d):
     for p in range(world):
         a, c = h1r[p].to(dev), h2r[p].to(dev)
         _lib.check(lib.maai_ntxent_normalize(a.data_ptr(), c.data_ptr(), b, d, 0, z_all[p].data_ptr(),
-                                             inv[p].data_ptr(), cos[p].data_ptr(), s), "k1")
+                                             inv[p].data_ptr(), cos[p].data_ptr(), None, 0, s), "k1")
     ref = O.positive_rank_oracle([h.numpy() for h in h1r], [h.numpy() for h in h2r])
     ol, _, _ = O.contrastive_loss_oracle_distributed([h.numpy() for h in h1r], [h.numpy() for h in h2r], 0.5, key_grad=False)
     for p in range(world):
@@ -128,13 +128,13 @@ def test_emulated_ranks_reduce_scatter_dataflow(world, b, d, tau):
     dh = [(h1r[p].to(dev), h2r[p].to(dev)) for p in range(world)]
     for p in range(world):
         _lib.check(lib.maai_ntxent_normalize(dh[p][0].data_ptr(), dh[p][1].data_ptr(), b, d, 0,
-                                             z_all[p].data_ptr(), inv[p].data_ptr(), cos[p].data_ptr(), s), "k1")
+                                             z_all[p].data_ptr(), inv[p].data_ptr(), cos[p].data_ptr(), None, 0, s), "k1")
     rowsum = torch.zeros(world, 2 * b, device=dev)
     r_loc = torch.zeros(world, 2 * b, device=dev)
     losses = torch.zeros(world, device=dev)
     for p in range(world):
         _lib.check(lib.maai_ntxent_fwd(z_all.data_ptr(), b, world, p, dp, 1.0 / tau, cos[p].data_ptr(),
-                                       rowsum[p].data_ptr(), r_loc[p].data_ptr(), losses[p:].data_ptr(), s), "k2")
+                                       rowsum[p].data_ptr(), r_loc[p].data_ptr(), losses[p:].data_ptr(), 0, s), "k2")
     # every rank's key-side partial sums for ALL anchors, then the reduce-scatter (sum over ranks)
     total = torch.zeros(world * 2 * b, dp, device=dev)
     for p in range(world):
@@ -186,20 +186,20 @@ def test_emulated_ranks_symmetric_forward(world, b, d, tau):
     for p in range(world):
         a, c = h1r[p].to(dev), h2r[p].to(dev)
         _lib.check(lib.maai_ntxent_normalize(a.data_ptr(), c.data_ptr(), b, d, 0, z_all[p].data_ptr(),
-                                             inv[p].data_ptr(), cos[p].data_ptr(), s), "k1")
+                                             inv[p].data_ptr(), cos[p].data_ptr(), None, 0, s), "k1")
     # reference: the full forward of every rank
     rowsum_full = torch.zeros(world, 2 * b, device=dev)
     r_full = torch.zeros(world, 2 * b, device=dev)
     loss_full = torch.zeros(world, device=dev)
     for p in range(world):
         _lib.check(lib.maai_ntxent_fwd(z_all.data_ptr(), b, world, p, dp, 1.0 / tau, cos[p].data_ptr(),
-                                       rowsum_full[p].data_ptr(), r_full[p].data_ptr(), loss_full[p:].data_ptr(), s), "k2")
+                                       rowsum_full[p].data_ptr(), r_full[p].data_ptr(), loss_full[p:].data_ptr(), 0, s), "k2")
     # symmetric: tile part of every rank, "barrier", then the finalize of every rank
     rowsum = torch.full((world, 2 * b), float("nan"), device=dev)
     stage = torch.full((world, world, 2 * b), float("nan"), device=dev)  # stage[p] = rank p's staging vectors
     for p in range(world):
         _lib.check(lib.maai_ntxent_fwd_sym_tiles(z_all.data_ptr(), b, world, p, dp, 1.0 / tau, rowsum[p].data_ptr(),
-                                                 stage[p].data_ptr(), s), "sym tiles")
+                                                 stage[p].data_ptr(), 0, s), "sym tiles")
     torch.cuda.synchronize()
     tab = torch.tensor([stage[p].data_ptr() for p in range(world)], dtype=torch.int64, device=dev)
     r_sym = torch.zeros(world, 2 * b, device=dev)

@@ -33,7 +33,7 @@ def test_native_library_is_loaded():
     lib = maai_b200._lib.load()
     before = lib.maai_launch_count()
     _run(np.random.randn(8, 16).astype(np.float32), np.random.randn(8, 16).astype(np.float32), 0.5)
-    assert lib.maai_launch_count() - before == 5  # normalise, fwd tile, finalise, bwd tile, dh
+    assert lib.maai_launch_count() - before == 4  # normalise (+ zero fill), fwd tile (+ finalise), bwd tile, dh
     maps = open("/proc/self/maps").read()
     assert "libmaai_ntxent.so" in maps
 
@@ -276,13 +276,13 @@ def test_c_abi_is_cuda_graph_capturable():
     def enqueue(stream):
         for t in steps:
             _lib.check(lib.maai_ntxent_normalize(t.h1.data_ptr(), t.h2.data_ptr(), b, d, 0, t.z.data_ptr(),
-                                                 t.inv.data_ptr(), t.cos.data_ptr(), stream), "k1")
+                                                 t.inv.data_ptr(), t.cos.data_ptr(), None, 0, stream), "k1")
             _lib.check(lib.maai_ntxent_fwd(t.z.data_ptr(), b, 1, 0, dp, 1.0 / tau, t.cos.data_ptr(), t.l.data_ptr(),
-                                           t.r.data_ptr(), t.loss.data_ptr(), stream), "k2")
+                                           t.r.data_ptr(), t.loss.data_ptr(), 0, stream), "k2")
             _lib.check(lib.maai_ntxent_bwd(t.z.data_ptr(), t.r.data_ptr(), t.r.data_ptr(), 1, t.l.data_ptr(),
                                            t.cos.data_ptr(), t.h1.data_ptr(), t.h2.data_ptr(), 0, t.inv.data_ptr(),
                                            one.data_ptr(), b, 1, 0, d, dp, 1.0 / tau, 3, t.g1.data_ptr(),
-                                           t.g2.data_ptr(), t.acc.data_ptr(), stream), "k3")
+                                           t.g2.data_ptr(), t.acc.data_ptr(), 0, stream), "k3")
 
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):

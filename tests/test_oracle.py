@@ -156,3 +156,36 @@ def test_top_k_accuracy_mirror_both_forms():
         assert float(a) == float(b) == float(c)
     with pytest.raises(TypeError):
         maai_b200.top_k_accuracy(logits, None, 1)
+
+
+@pytest.mark.parametrize("world,b,d,tau", [(1, 300, 32, 0.5), (3, 100, 16, 0.1), (4, 64, 128, 0.2)])
+def test_sampled_rows_oracle_matches_full_oracle(world, b, d, tau):
+    """The sampled-anchor oracle used at BASELINE's full sizes (ntxent_rows_oracle: sampled pairs of one
+    rank x all 2B keys) is the full oracle restricted to those rows -- loss terms, both gradient
+    semantics -- and the plain-torch all-row denominators (oracle/large_batch.py) agree with fp64."""
+    from oracle.large_batch import den_all_torch
+    rng = np.random.default_rng(world * 10 + b)
+    B = world * b
+    H1 = rng.standard_normal((B, d))
+    H2 = H1 + 0.5 * rng.standard_normal((B, d))
+    h1r = [H1[p * b:(p + 1) * b] for p in range(world)]
+    h2r = [H2[p * b:(p + 1) * b] for p in range(world)]
+    den = O.row_denominators(H1, H2, tau)
+    den_t = den_all_torch(torch.from_numpy(H1), torch.from_numpy(H2), tau, block=77).numpy()
+    assert np.abs(den_t / den - 1).max() < 1e-5  # fp32 matmul + exp
+    for kg in (True, False):
+        ol, o1, o2 = O.contrastive_loss_oracle_distributed(h1r, h2r, tau, key_grad=kg)
+        for p in range(world):
+            pairs = rng.choice(b, 17, replace=False)
+            r = O.ntxent_rows_oracle(H1, H2, pairs, tau, rank=p, world=world, den_all=den if kg else None,
+                                     key_grad=kg, block=5)
+            assert np.abs(r["dh1"] - o1[p][pairs]).max() <= 1e-10 * np.abs(o1[p]).max()
+            assert np.abs(r["dh2"] - o2[p][pairs]).max() <= 1e-10 * np.abs(o2[p]).max()
+            assert abs(O.loss_from_denominators(H1, H2, den, tau, p, world) - ol[p]) <= 1e-10 * abs(ol[p])
+            own = p * b + pairs
+            assert np.abs(r["den"][0] / den[own] - 1).max() < 1e-12 and np.abs(r["den"][1] / den[B + own] - 1).max() < 1e-12
+    if world == 1:
+        loss, g1, g2 = O.contrastive_loss_oracle(H1, H2, tau)
+        r = O.ntxent_rows_oracle(H1, H2, np.arange(b), tau)
+        assert abs(r["terms"].sum() / b - loss) <= 1e-12 * abs(loss)
+        assert rel_fro(r["dh1"], g1) < 1e-12 and rel_fro(r["dh2"], g2) < 1e-12
