@@ -11,8 +11,17 @@ pairs x d=128, tau=0.5, both inputs requiring grad, row-sharded over the N ranks
 it fits one GPU because the 2Bx2B logit matrix is never materialised.  configs[1] (4096 pairs) is
 reported as a secondary number inside ``config`` at N=1.
 
+Before anything is timed, a PARITY GATE runs at every N on the bench shape itself: one step of the
+product path (the same gather mode / forward schedule the timed region uses), its per-rank loss and
+the dH rows of sampled pairs of every rank against the fp64 oracle (oracle/ntxent_oracle.py
+ntxent_rows_oracle; the all-row softmax denominators the key-side term needs come from plain torch
+fp32 ops, validated against fp64 on the sampled rows).  Errors are all-reduced (MAX) and reported
+under "parity"; above the north-star tolerances (loss 1e-3, dH 1e-2) the run exits non-zero.  The
+oracle is used there only as the checker.
+
 Prints ONE JSON line on rank 0 (see the keys below).  ``--impl reference`` times the reference's
-own CPU implementation of the path (the torch port in oracle/, all host threads) on a bounded
+own CPU implementation of the path -- the UNMODIFIED reference file (oracle/_ref/Objective.py, a
+build-time copy; the torch port of oracle/ if that copy is absent), all host threads -- on a bounded
 sample of the same workload.
 """
 from __future__ import annotations
@@ -100,15 +109,14 @@ class ClockSampler:
 
 
 def run_reference(args, rank):
-    """CPU arm: the reference's own implementation (torch port) on all host threads."""
+    """CPU arm: the reference's own implementation on all host threads (oracle/ref_runner.py)."""
     if rank != 0:
         return
-    from oracle.cpu_baseline import time_port_stripe
+    from oracle.ref_runner import time_reference_stripe
     import torch
     b_sample = 256
-    r = time_port_stripe(PAIRS, DIM, TAU, b_sample, steps=args.steps, warmup=max(args.warmup, 2))
-    sample = (f"stripe of {r['b_sample']} anchor pairs x all {PAIRS} global keys per step, fwd+bwd "
-              f"(keys constant as in the reference's world_size>1 branch), torch {torch.__version__} fp32")
+    r = time_reference_stripe(PAIRS, DIM, TAU, b_sample, steps=args.steps, warmup=max(args.warmup, 2))
+    sample = reference_sample_text(r, PAIRS, torch.__version__)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["pairs_per_s"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 2),
@@ -116,12 +124,22 @@ def run_reference(args, rank):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(PAIRS, DIM, TAU), "pairs_global": PAIRS, "dim": DIM,
                    "temperature": TAU},
-        "cpu_baseline": {"value": r["pairs_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+        "cpu_baseline": {"value": r["pairs_per_s"], "unit": UNIT, "cores": r["threads"], "kind": r["kind"],
                          "sample": sample},
         "e2e": {"value": r["pairs_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def reference_sample_text(r, pairs, torch_version):
+    if r["kind"] == "reference":
+        return (f"UNMODIFIED reference SimCLR/Objective.py::contrastive_loss, one rank's share of the {pairs}-pair "
+                f"workload per step: {r['b_sample']} anchor pairs x all {pairs} gathered keys through its own "
+                f"world_size={r['world_emulated']} branch (Objective.py:51-58), fwd+bwd; dist.all_gather replaced by a "
+                f"local fill from constant keys; torch {torch_version} fp32 CPU, {r['s_per_step']:.3f} s/step")
+    return (f"torch port of the reference (oracle/_ref absent): stripe of {r['b_sample']} anchor pairs x all {pairs} "
+            f"global keys per step, fwd+bwd, torch {torch_version} fp32 CPU, {r['s_per_step']:.3f} s/step")
 
 
 def emit(line):
@@ -149,6 +167,10 @@ def main():
     ap.add_argument("--tau", type=float, default=TAU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity gate (profiling runs only)")
+    ap.add_argument("--parity-pairs", type=int, default=256, help="sampled pairs over all ranks in the parity gate")
+    ap.add_argument("--require-peer", action="store_true",
+                    help="N > 1: fail unless the fused NVLink peer-store gathers are the mode that ran")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -160,6 +182,7 @@ def main():
         run_reference(args, rank)
         return
 
+    import numpy as np
     import torch
     import torch.distributed as dist
     import maai_b200
@@ -176,16 +199,27 @@ def main():
     lib = maai_b200._lib.load()
     peaks = load_peaks()
 
-    from maai_b200.Objective import _peer_state
+    from maai_b200 import Objective as P
 
-    def peer_mode_used():  # decided (and voted on by the ranks) at the first call with a given shape
-        return world > 1 and any(v for k, v in _peer_state.items() if isinstance(k, tuple) and k[0] == "usable")
     B, d, tau = args.pairs, args.dim, args.tau
     assert B % world == 0
     b = B // world
+    dp = maai_b200.padded_dim(d)
 
-    def make_inputs(bb):
-        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    def path_used(bb):
+        """Which dataflow the public API takes for bb pairs per rank (decided at the first call per shape)."""
+        if world == 1:
+            return dict(gather_mode="single rank", sym_forward=bool(lib.maai_ntxent_fwd_is_symmetric(bb, 1, dp)))
+        key = ("usable", bb, dp, world, rank, str(dev), id(None))
+        peer = bool(P._peer_state.get(key))
+        if not peer:
+            return dict(gather_mode="nccl all_gather_into_tensor", sym_forward=False)
+        ws = P.PeerWorkspace.get(bb, dp, world, rank, dev, None)
+        return dict(gather_mode="peer stores, NVSwitch multicast" if ws.mc_z[0] else "peer stores, unicast",
+                    sym_forward=bool(P._sym_forward_enabled(bb, dp, world)))
+
+    def make_inputs(bb, r=None):
+        g = torch.Generator(device=dev).manual_seed(1234 + (rank if r is None else r))
         return (torch.randn(bb, d, generator=g, device=dev), torch.randn(bb, d, generator=g, device=dev))
 
     def barrier():
@@ -193,17 +227,72 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(vals):
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step(x, y):
         x.grad = None
         y.grad = None
         loss, _, _ = maai_b200.contrastive_loss(x, y, temperature=tau, local_rank=rank, world_size=world,
-                                                device=dev)
+                                                device=dev, key_grad=True)
         loss.backward()
         return loss
 
-    def timed_run(bb, steps, warmup, profile, grad1=True):
+    # ---------------- parity gate: the bench shape, every N, before anything is timed ----------------
+    def parity_gate():
+        from oracle import ntxent_oracle as O          # the checker, never the thing measured
+        from oracle.large_batch import den_all_torch
+        parts = [make_inputs(b, r) for r in range(world)]   # every rank regenerates the global batch
+        H1 = torch.cat([p[0] for p in parts])
+        H2 = torch.cat([p[1] for p in parts])
+        den_all = den_all_torch(H1, H2, tau).cpu().numpy()
+        H1c, H2c = H1.cpu().numpy(), H2.cpu().numpy()
+        n = max(16, args.parity_pairs // world)
+        rng = np.random.default_rng(99 + rank)
+        pairs = np.unique(np.concatenate([rng.choice(b, min(n, b), replace=False), [0, b - 1]]))
+        ref = O.ntxent_rows_oracle(H1c, H2c, pairs, tau, rank=rank, world=world, den_all=den_all)
+        own = rank * b + pairs
+        den_err = max(np.abs(den_all[own] / ref["den"][0] - 1).max(), np.abs(den_all[B + own] / ref["den"][1] - 1).max())
+        loss_ref = O.loss_from_denominators(H1c, H2c, den_all, tau, rank, world)
+        x = parts[rank][0].clone().requires_grad_(True)
+        y = parts[rank][1].clone().requires_grad_(True)
+        loss = step(x, y)
+        torch.cuda.synchronize()
+        g1, g2 = x.grad[pairs].double().cpu().numpy(), y.grad[pairs].double().cpu().numpy()
+        fro = lambda a, r_: float(np.linalg.norm(a - r_) / np.linalg.norm(r_))
+        mx = lambda a, r_: float(np.abs(a - r_).max() / np.abs(r_).max())
+        e = allmax([abs(float(loss) - loss_ref) / abs(loss_ref), max(fro(g1, ref["dh1"]), fro(g2, ref["dh2"])),
+                    max(mx(g1, ref["dh1"]), mx(g2, ref["dh2"])), den_err,
+                    0.0 if bool(torch.isfinite(x.grad).all() and torch.isfinite(y.grad).all()) else 1.0])
+        out = {"loss_rel": e[0], "dh_rel_fro": e[1], "dh_rel_max": e[2], "rows": int(2 * len(pairs) * world),
+               "pairs_per_rank": int(len(pairs)), "ranks": world, "reduction": "max over ranks",
+               "torch_fp32_denominators_vs_fp64": e[3], "all_finite": e[4] == 0.0,
+               "oracle": "oracle/ntxent_oracle.py::ntxent_rows_oracle (fp64, sampled pairs of every rank x all keys) "
+                         "+ loss_from_denominators", "tolerance": {"loss_rel": 1e-3, "dh_rel_fro": 1e-2},
+               "loss": float(loss), "loss_oracle_rank0": loss_ref if rank == 0 else None}
+        out.update(path_used(b))
+        out["ok"] = bool(e[0] <= 1e-3 and e[1] <= 1e-2 and e[2] <= 2e-2 and e[3] <= 1e-4 and e[4] == 0.0)
+        return out
+
+    parity = None
+    if not args.no_parity:
+        parity = parity_gate()
+        if not parity["ok"]:
+            if rank == 0:
+                sys.stderr.write("PARITY GATE FAILED: " + json.dumps(parity) + "\n")
+                emit({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world, "parity": parity,
+                      "error": "parity gate failed; nothing was timed"})
+            raise SystemExit(3)
+    if args.require_peer and world > 1 and not path_used(b)["gather_mode"].startswith("peer"):
+        raise SystemExit("--require-peer: the fused peer-store gathers are not the mode that ran: "
+                         + json.dumps(path_used(b)))
+
+    def timed_run(bb, steps, warmup, profile, grad1=True, sample_clocks=False):
         h1, h2 = make_inputs(bb)
         x = h1.requires_grad_(grad1)
         y = h2.requires_grad_(True)
@@ -212,6 +301,9 @@ def main():
         barrier()
         _Profiler.reset()
         _Profiler.enabled = profile
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
         launches0 = lib.maai_launch_count()
         evs = []
         for _ in range(steps):
@@ -223,6 +315,7 @@ def main():
             e.record()
             evs.append((a, e))
         barrier()
+        clocks = sampler.stop() if sampler else None
         _Profiler.enabled = False
         launches = lib.maai_launch_count() - launches0
         ms = [a.elapsed_time(e) for a, e in evs]
@@ -233,7 +326,7 @@ def main():
             total_ms = float(t)
         spans = {k: [a.elapsed_time(e) for a, e in v] for k, v in _Profiler.events.items()}
         return dict(ms_per_step=total_ms / steps, ms_median=statistics.median(ms), launches=launches,
-                    spans=spans, loss=float(loss.detach()))
+                    spans=spans, loss=float(loss.detach()), clocks=clocks)
 
     def timed_graphed(bb, steps, warmup):
         """same step through maai_b200.GraphedNTXentLoss (forward and backward as one CUDA graph each)"""
@@ -264,80 +357,81 @@ def main():
         return dict(ms_per_step=sum(ms) / steps, loss=float(loss.detach()))
 
     # ---------------- main timed region (device-resident inputs) ----------------
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    main_r = timed_run(b, args.steps, args.warmup, profile=True)
-    clocks = sampler.stop() if rank == 0 else None
+    main_r = timed_run(b, args.steps, args.warmup, profile=True, sample_clocks=True)
+    clocks = main_r["clocks"]
+    # the same step at the other run length: short runs see boost clocks (~1.9 GHz), 200 back-to-back steps
+    # run into the power cap (MEASURED_PEAKS: burst vs sustained) -- both are reported with their clocks
+    other_steps = 20 if args.steps >= 100 else 200
+    other_r = timed_run(b, other_steps, args.warmup, profile=False, sample_clocks=True)
 
     # ---------------- end to end through the public API with HOST buffers ----------------
-    # Every step copies ITS inputs pinned host -> device and ITS results (loss, dh1, dh2) device ->
-    # pinned host.  "pipelined": the copies run on a copy stream, double-buffered, so the H2D of step
-    # i+1 and the D2H of step i-1 overlap the kernels of step i (what an input pipeline with prefetch
-    # does); "serial": one stream, copy -> compute -> copy -> host sync per step.
+    # Every step copies ITS inputs pinned host -> device and ITS results (loss, dh1, dh2) device -> pinned
+    # host.  One packed pinned input [h1|h2] -> ONE H2D copy per step on its own stream; the results go into
+    # one packed pinned buffer [dh1|dh2|loss] on a third stream, so both DMA directions overlap the kernels
+    # of the neighbouring steps (what an input pipeline with prefetch does).  "serial": one stream, copy ->
+    # compute -> copy -> host sync per step.
     g = torch.Generator().manual_seed(1234 + rank)
-    hp1 = torch.randn(b, d, generator=g).pin_memory()
-    hp2 = torch.randn(b, d, generator=g).pin_memory()
-    out_g1 = [torch.empty(b, d).pin_memory() for _ in range(2)]
-    out_g2 = [torch.empty(b, d).pin_memory() for _ in range(2)]
-    out_loss = [torch.empty(()).pin_memory() for _ in range(2)]
+    n_in = b * d
+    h_in = torch.empty(2, b, d).pin_memory()
+    h_in[0].copy_(torch.randn(b, d, generator=g))
+    h_in[1].copy_(torch.randn(b, d, generator=g))
+    h_out = [torch.empty(2 * n_in + 1).pin_memory() for _ in range(2)]
+    d_in = [torch.empty(2, b, d, device=dev) for _ in range(2)]
 
     def e2e_serial_step():
-        x = hp1.to(dev, non_blocking=True).requires_grad_(True)
-        y = hp2.to(dev, non_blocking=True).requires_grad_(True)
+        d_in[0].copy_(h_in, non_blocking=True)
+        x = d_in[0][0].detach().requires_grad_(True)
+        y = d_in[0][1].detach().requires_grad_(True)
         loss, _, _ = maai_b200.contrastive_loss(x, y, temperature=tau, local_rank=rank, world_size=world,
-                                                device=dev)
+                                                device=dev, key_grad=True)
         loss.backward()
-        out_loss[0].copy_(loss.detach(), non_blocking=True)
-        out_g1[0].copy_(x.grad, non_blocking=True)
-        out_g2[0].copy_(y.grad, non_blocking=True)
+        h_out[0][:n_in].copy_(x.grad.view(-1), non_blocking=True)
+        h_out[0][n_in:2 * n_in].copy_(y.grad.view(-1), non_blocking=True)
+        h_out[0][2 * n_in:].copy_(loss.detach().view(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the host results every step
 
-    copy_s = torch.cuda.Stream(device=dev)
+    in_s = torch.cuda.Stream(device=dev)
+    out_s = torch.cuda.Stream(device=dev)
     main_s = torch.cuda.current_stream()
-
-    def h2d():
-        """inputs of one step on the copy stream; returns (x, y, event)"""
-        with torch.cuda.stream(copy_s):
-            x = hp1.to(dev, non_blocking=True)
-            y = hp2.to(dev, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_s)
-        return x, y, ev
+    ev_in = [torch.cuda.Event() for _ in range(2)]      # inputs of the slot are on the device
+    ev_free = [torch.cuda.Event() for _ in range(2)]    # the step that read the slot's inputs has finished
+    ev_done = [torch.cuda.Event() for _ in range(2)]    # results of the slot are computed
+    ev_out = [torch.cuda.Event() for _ in range(2)]     # results of the slot are on the host
 
     def e2e_pipelined(steps):
-        nxt = h2d()
-        pending = []  # (event, slot) of result copies in flight
+        def h2d(i):
+            s_ = i & 1
+            with torch.cuda.stream(in_s):
+                if i >= 2:
+                    in_s.wait_event(ev_free[s_])
+                d_in[s_].copy_(h_in, non_blocking=True)
+                ev_in[s_].record(in_s)
+        h2d(0)
         for i in range(steps):
-            x, y, ev = nxt
-            main_s.wait_event(ev)
-            x.record_stream(main_s)
-            y.record_stream(main_s)
+            s_ = i & 1
             if i + 1 < steps:
-                nxt = h2d()  # prefetch the next step's inputs while this step computes
-            x.requires_grad_(True)
-            y.requires_grad_(True)
+                h2d(i + 1)  # prefetch the next step's inputs while this step computes
+            main_s.wait_event(ev_in[s_])
+            x = d_in[s_][0].detach().requires_grad_(True)
+            y = d_in[s_][1].detach().requires_grad_(True)
             loss, _, _ = maai_b200.contrastive_loss(x, y, temperature=tau, local_rank=rank, world_size=world,
-                                                    device=dev)
+                                                    device=dev, key_grad=True)
             loss.backward()
-            done = torch.cuda.Event()
-            done.record(main_s)
-            slot = i & 1
-            if len(pending) == 2:  # the host buffers of this slot must have been read back
-                pending.pop(0)[0].synchronize()
-            with torch.cuda.stream(copy_s):
-                copy_s.wait_event(done)
+            ev_free[s_].record(main_s)
+            ev_done[s_].record(main_s)
+            if i >= 2:
+                ev_out[s_].synchronize()  # the host has consumed this slot's previous results
+            with torch.cuda.stream(out_s):
+                out_s.wait_event(ev_done[s_])
                 lg, g1, g2 = loss.detach(), x.grad, y.grad
                 for tns in (lg, g1, g2):
-                    tns.record_stream(copy_s)
-                out_loss[slot].copy_(lg, non_blocking=True)
-                out_g1[slot].copy_(g1, non_blocking=True)
-                out_g2[slot].copy_(g2, non_blocking=True)
-                fin = torch.cuda.Event()
-                fin.record(copy_s)
-            pending.append((fin, slot))
-        for fin, _ in pending:
-            fin.synchronize()
+                    tns.record_stream(out_s)
+                h_out[s_][:n_in].copy_(g1.view(-1), non_blocking=True)
+                h_out[s_][n_in:2 * n_in].copy_(g2.view(-1), non_blocking=True)
+                h_out[s_][2 * n_in:].copy_(lg.view(1), non_blocking=True)
+                ev_out[s_].record(out_s)
+        for s_ in range(min(2, steps)):
+            ev_out[s_].synchronize()
 
     def timed_e2e(fn_steps):
         barrier()
@@ -356,8 +450,7 @@ def main():
     e2e_pipelined(args.warmup)
     e2e_serial_s = timed_e2e(lambda k: [e2e_serial_step() for _ in range(k)])
     e2e_pipe_s = timed_e2e(e2e_pipelined)
-    # headline = the faster schedule (with several ranks on one host the second copy stream can lose:
-    # N=2 measured 3.4 ms pipelined vs 2.0 ms serial)
+    e2e_loss = float(h_out[(args.steps - 1) & 1][2 * n_in])
     e2e_s = min(e2e_pipe_s, e2e_serial_s)
     e2e_mode = "pipelined" if e2e_pipe_s <= e2e_serial_s else "serial"
     e2e_pairs = B * args.steps / e2e_s
@@ -369,11 +462,29 @@ def main():
     if world == 1 and not args.no_secondary and B != 4096:
         s = timed_run(4096, max(args.steps, 50), args.warmup, profile=False)
         secondary = {"workload": workload_name(4096, d, tau), "ms_per_step": s["ms_per_step"],
-                     "pairs_per_s": 4096 / (s["ms_per_step"] * 1e-3),
+                     "pairs_per_s": 4096 / (s["ms_per_step"] * 1e-3), "gpu_launches_per_step": s["launches"] / max(args.steps, 50),
                      "frac_bf16_peak": 24.0 * 4096 ** 2 * d / (s["ms_per_step"] * 1e-3) / (peaks["bf16"] * 1e12)}
         sg = timed_graphed(4096, max(args.steps, 50), args.warmup)
         secondary["cuda_graph_ms_per_step"] = sg["ms_per_step"]
         secondary["cuda_graph_pairs_per_s"] = 4096 / (sg["ms_per_step"] * 1e-3)
+        secondary["cuda_graph_frac_bf16_peak"] = 24.0 * 4096 ** 2 * d / (sg["ms_per_step"] * 1e-3) / (peaks["bf16"] * 1e12)
+        # "vs reference PyTorch loss" (BASELINE.json configs[1]): the unmodified reference on this GPU
+        try:
+            from oracle.ref_runner import time_reference_full
+            for nref in (4096, 16384):
+                tr = time_reference_full(nref, d, tau, steps=5, warmup=2, device=dev)
+                if tr is None:
+                    break
+                secondary[f"torch_gpu_reference_{nref}_pairs"] = {
+                    "what": "UNMODIFIED reference contrastive_loss(device='cuda') fwd+bwd on this B200, fp32 (TF32 off), "
+                            "host wall clock with a device sync per step, median of 5",
+                    "ms_per_step": tr["s_per_step"] * 1e3, "pairs_per_s": tr["pairs_per_s"], "loss": tr["loss"]}
+                torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001  (out of memory on a shared box must not kill the bench line)
+            secondary["torch_gpu_reference_error"] = repr(ex)[:200]
+        if secondary.get("torch_gpu_reference_4096_pairs"):
+            secondary["speedup_vs_torch_gpu_reference"] = (secondary["torch_gpu_reference_4096_pairs"]["ms_per_step"]
+                                                           / s["ms_per_step"])
 
     # ---------------- secondary: the reference's training call, hidden1 detached ----------------
     # (Contrastive_Learning.py:685-690 passes hidden1=outputs1.data: only dh2 is needed, half of the backward)
@@ -386,26 +497,25 @@ def main():
     # ---------------- secondary: configs[0] (256 pairs, the reference's own CPU-runnable case) ----------------
     configs0 = None
     if rank == 0 and world == 1 and not args.no_secondary and not args.no_cpu_baseline:
-        from oracle.cpu_baseline import time_port_full
+        from oracle.ref_runner import time_reference_full
         s0 = timed_run(256, max(args.steps, 100), args.warmup, profile=False)
-        c0 = time_port_full(256, d, tau, steps=30, warmup=5)
+        c0 = time_reference_full(256, d, tau, steps=30, warmup=5)
         g0 = timed_graphed(256, max(args.steps, 100), args.warmup)
         configs0 = {"workload": workload_name(256, d, tau), "ms_per_step": s0["ms_per_step"],
                     "pairs_per_s": 256 / (s0["ms_per_step"] * 1e-3), "loss": s0["loss"],
                     "cuda_graph_ms_per_step": g0["ms_per_step"], "cuda_graph_pairs_per_s": 256 / (g0["ms_per_step"] * 1e-3),
-                    "cpu_reference_port": {"ms_per_step": c0["s_per_step"] * 1e3, "pairs_per_s": c0["pairs_per_s"],
-                                           "cores": c0["threads"], "loss": c0["loss"]},
-                    "note": "host-launch-bound on the GPU (9 launches from Python per step); different random "
+                    "cpu_reference": {"kind": c0["kind"], "ms_per_step": c0["s_per_step"] * 1e3,
+                                      "pairs_per_s": c0["pairs_per_s"], "cores": c0["threads"], "loss": c0["loss"]},
+                    "note": "host-launch-bound on the GPU (4 launches from Python per step); different random "
                             "draws on the two devices, parity at this shape is tests/test_gpu_parity.py"}
 
     # ---------------- CPU baseline (rank 0, N=1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.cpu_baseline import time_port_stripe
-        r = time_port_stripe(B, d, tau, 256, steps=10, warmup=2)
-        cpu = {"value": r["pairs_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
-               "sample": f"10 steps of a stripe of {r['b_sample']} anchor pairs x all {B} global keys, fwd+bwd, "
-                         f"torch {torch.__version__} fp32 CPU ({r['s_per_step']:.3f} s/step)"}
+        from oracle.ref_runner import time_reference_stripe
+        r = time_reference_stripe(B, d, tau, 256, steps=10, warmup=2)
+        cpu = {"value": r["pairs_per_s"], "unit": UNIT, "cores": r["threads"], "kind": r["kind"],
+               "sample": "10 steps; " + reference_sample_text(r, B, torch.__version__)}
 
     if rank == 0:
         ms = main_r["ms_per_step"]
@@ -419,48 +529,59 @@ def main():
         step_tflops = 24.0 * B * B * d / (ms * 1e-3) / 1e12 / world
         traffic = None
         try:  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
                 tj = json.load(f).get(f"pairs={B},dim={d},n_gpus={world}", {})
             traffic = next((v for k, v in tj.items() if "BWD" in k), None)
         except Exception:
             traffic = None
+        used = path_used(b)
+        short, long_ = (other_r, main_r) if args.steps >= 100 else (main_r, other_r)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(B, d, tau), "pairs_global": B, "pairs_per_gpu": b,
                        "dim": d, "temperature": tau,
-                       "parallelism": f"dp{world}: anchor rows sharded, bf16 all-gather of z, fp32 all-gather of row factors"
-                                      + ((" -- both fused into the producing kernels as NVLink peer stores + symmetric-memory barrier"
-                                          if peer_mode_used() else " -- NCCL all_gather_into_tensor") if world > 1 else ""),
+                       "parallelism": f"dp{world}: anchor rows sharded, bf16 gather of z, fp32 gather of row factors"
+                                      + (f" -- {used['gather_mode']}" if world > 1 else ""),
+                       "gather_mode": used["gather_mode"], "sym_forward": used["sym_forward"],
                        "l2": "flushed between timed steps (256 MiB write outside the event bracket)",
                        "step_tflops_per_gpu_algorithmic": step_tflops,
                        "step_frac_bf16_peak": step_tflops / peaks["bf16"],
-                       # executed flops: a single rank runs the symmetric forward (half the forward's MMAs)
-                       "step_tflops_per_gpu_executed": step_tflops * ((20.0 / 24.0) if (world == 1 and maai_b200.padded_dim(d) <= 128) else 1.0),
+                       # executed flops: the symmetric forward runs half the forward's MMAs
+                       "step_tflops_per_gpu_executed": step_tflops * ((20.0 / 24.0) if used["sym_forward"] else 1.0),
                        "ms_median": main_r["ms_median"], "loss": main_r["loss"],
                        "fwd_call_ms": fwd_ms, "bwd_call_ms": bwd_ms,
-                       "span_ms_mean": {k: (statistics.mean(v) if v else None) for k, v in main_r["spans"].items()}},
+                       "span_ms_mean": {k: (statistics.mean(v) if v else None) for k, v in main_r["spans"].items()},
+                       "run_lengths": {
+                           "short": {"steps": min(args.steps, other_steps), "ms_per_step": short["ms_per_step"],
+                                     "pairs_per_s": B / (short["ms_per_step"] * 1e-3), "clocks": short["clocks"]},
+                           "sustained": {"steps": max(args.steps, other_steps), "ms_per_step": long_["ms_per_step"],
+                                         "pairs_per_s": B / (long_["ms_per_step"] * 1e-3), "clocks": long_["clocks"],
+                                         "frac_bf16_peak_sustained": (24.0 * B * B * d / (long_["ms_per_step"] * 1e-3) / 1e12 / world
+                                                                      / peaks["bf16_sustained"]) if peaks["bf16_sustained"] else None}}},
             "clocks": clocks,
+            "parity": parity,
             "e2e": {"value": e2e_pairs, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s / args.steps * 1e3,
-                    "schedule": e2e_mode,
+                    "schedule": e2e_mode, "loss_read_on_host": e2e_loss,
                     "pipelined_ms_per_step": e2e_pipe_s / args.steps * 1e3,
                     "serial_value": B * args.steps / e2e_serial_s,
                     "serial_ms_per_step": e2e_serial_s / args.steps * 1e3,
-                    "what": "every step: pinned host h1,h2 -> device, contrastive_loss + backward, loss + dh1 + dh2 -> "
-                            "pinned host; wall clock over all steps.  Two schedules are timed and value is the faster one "
-                            "(schedule): pipelined = copies on a second stream, double-buffered (H2D of step i+1 / D2H of "
-                            "step i-1 overlap the kernels of step i); serial = one stream, host sync after every step"},
+                    "what": "every step: ONE pinned host buffer [h1|h2] -> device, contrastive_loss + backward, "
+                            "[dh1|dh2|loss] -> ONE pinned host buffer; wall clock over all steps, max over ranks.  Two "
+                            "schedules are timed and value is the faster one (schedule): pipelined = H2D and D2H on their "
+                            "own streams, double-buffered (H2D of step i+1 / D2H of step i-1 overlap the kernels of step "
+                            "i); serial = one stream, host sync after every step"},
             "gpu_launches": int(main_r["launches"]),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["bf16"]) if achieved else None, "traffic": traffic,
-                         "traffic_note": "dram read+write bytes per launch, ncu --set full (profiles/r1_ncu_summary_v10.md): one pass "
-                                         "over z (16.8 MB) + the fp32 accumulator lines the atomics touch (33.5 MB); the "
+                         "traffic_note": "dram read+write bytes per launch, ncu --set full (profiles/r2_ncu_summary_*.md): one pass "
+                                         "over z + the fp32 accumulator lines the atomics touch; the "
                                          "2Bx2B logits never reach HBM (the reference moves ~100*b*B bytes)",
-                         "kernel": f"ntxent_tile_kernel<D={maai_b200.padded_dim(d)},BWD,NQ=1>",
+                         "kernel": f"ntxent_tile_kernel<D={dp},BWD,NQ=1>",
                          "how": "16*b*B*d algorithmic flops / mean CUDA-event time of the maai_ntxent_bwd call "
-                                "(memset + tile kernel + dh kernel) over the timed steps",
+                                "(tile kernel + dh kernel) over the timed steps",
                          "peak_source": peaks["source"] + ", burst cuBLAS bf16",
                          "peak_sustained": peaks["bf16_sustained"]},
             "cpu_baseline": cpu,

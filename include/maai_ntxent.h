@@ -103,6 +103,22 @@ int maai_ntxent_normalize_peer(const void* h1, const void* h2, int b, int d, int
                                const void* const* peer_z_bases, void* mc_z_base, int world, int rank,
                                float* inv_norm, float* pos_cos, void* zero_fill, size_t zero_bytes, void* stream);
 
+/* K1 for CHAINED VIEWS: the reference's training loop passes this step's
+ * outputs2 to the next step as hidden1 ("outputs1 = outputs2", Contrastive_Learning.py:700; consumed
+ * detached, :685), so the view-a rows of every rank at step t are the view-b rows of step t-1 that every
+ * rank already holds, normalised and in bf16, in its gathered key buffer of step t-1.  Reads only h2:
+ * normalises it into the view-b rows (local store, peer stores or multicast exactly as above: HALF the
+ * gather payload), copies the view-b rows of all `world` slots of z_prev into the view-a rows of z_new
+ * (local copy) and carries the view-a 1/norm over from inv_norm_prev.  hidden1 must not require grad.
+ *   z_prev         (world, 2b, d_pad) bf16: the previous step's gathered buffer (this rank's copy)
+ *   inv_norm_prev  (2b) the previous step's inv_norm
+ *   z_new          (world, 2b, d_pad) bf16: this rank's buffer of this step (!= z_prev)
+ *   peer_z_bases / mc_z_base   as in maai_ntxent_normalize_peer, or NULL / NULL (view b stored into z_new) */
+int maai_ntxent_normalize_chain(const void* h2, int b, int d, int in_dtype, const void* z_prev,
+                                const float* inv_norm_prev, void* z_new, const void* const* peer_z_bases,
+                                void* mc_z_base, int world, int rank, float* inv_norm, float* pos_cos,
+                                void* zero_fill, size_t zero_bytes, void* stream);
+
 /* K2 fused with the all-gather of the row factors: like maai_ntxent_fwd, but r_i is stored into slot
  * `rank` of every rank's gathered r array (maai_ntxent_r_len floats each, zero padded by the owner).
  *   peer_r_bases  DEVICE array of `world` peer-mapped base addresses of the r arrays

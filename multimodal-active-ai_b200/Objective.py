@@ -311,7 +311,10 @@ class _NTXentFunction(torch.autograd.Function):
     """loss = NT-Xent(hidden1, hidden2) for this rank (Objective.py:79), autograd-compatible."""
 
     @staticmethod
-    def forward(ctx, hidden1, hidden2, temperature, rank, world, group, key_grad, stash, peer=False):
+    def forward(ctx, hidden1, hidden2, temperature, rank, world, group, key_grad, stash, peer=False, chain=None,
+                carry=None):
+        # chain: {"z_all", "inv_norm"} of the previous step when hidden1 IS that step's hidden2 (chained views,
+        # maai_ntxent_normalize_chain); carry: dict that receives this step's {"z_all", "inv_norm"}
         lib = _lib.load()
         b, d = hidden1.shape
         dev = hidden1.device
@@ -331,7 +334,7 @@ class _NTXentFunction(torch.autograd.Function):
         with _on_device(dev):
             if peer and world > 1:
                 return _NTXentFunction._forward_peer(ctx, h1, h2, dt, inv_tau, rank, world, group, needs_grad,
-                                                     full, stash)
+                                                     full, stash, chain, carry)
             st = _stream(dev)
             z_all = torch.empty((world, 2 * b, dp), dtype=torch.bfloat16, device=dev)
             ws, rowsum, dz_acc = _step_workspace(lib, b, dp, needs_grad, dev)
@@ -350,9 +353,17 @@ class _NTXentFunction(torch.autograd.Function):
                 r_row = None
 
             with _Profiler.span("normalize"):
-                _lib.check(lib.maai_ntxent_normalize(_ptr(h1), _ptr(h2), b, d, dt, _ptr(z_all[rank]),
-                                                     _ptr(inv_norm), _ptr(pos_cos), _ptr(ws), ws.numel() * 4, st),
-                           "maai_ntxent_normalize")
+                if chain is not None:
+                    _lib.check(lib.maai_ntxent_normalize_chain(_ptr(h2), b, d, dt, _ptr(chain["z_all"]),
+                                                               _ptr(chain["inv_norm"]), _ptr(z_all), None, None, world,
+                                                               rank, _ptr(inv_norm), _ptr(pos_cos), _ptr(ws),
+                                                               ws.numel() * 4, st), "maai_ntxent_normalize_chain")
+                else:
+                    _lib.check(lib.maai_ntxent_normalize(_ptr(h1), _ptr(h2), b, d, dt, _ptr(z_all[rank]),
+                                                         _ptr(inv_norm), _ptr(pos_cos), _ptr(ws), ws.numel() * 4, st),
+                               "maai_ntxent_normalize")
+            if carry is not None:
+                carry["z_all"], carry["inv_norm"] = z_all, inv_norm
             with _Profiler.span("gather_z"):
                 gather_rows(z_all, rank, group)
             with _Profiler.span("fwd"):
@@ -375,7 +386,7 @@ class _NTXentFunction(torch.autograd.Function):
         return loss
 
     @staticmethod
-    def _forward_peer(ctx, h1, h2, dt, inv_tau, rank, world, group, needs_grad, full, stash):
+    def _forward_peer(ctx, h1, h2, dt, inv_tau, rank, world, group, needs_grad, full, stash, chain=None, carry=None):
         """world > 1 with the gathers fused into the producing kernels (PeerWorkspace)."""
         lib = _lib.load()
         b, d = h1.shape
@@ -393,10 +404,18 @@ class _NTXentFunction(torch.autograd.Function):
         if extra_barrier:  # the previous user of this set ran its backward late: see PeerWorkspace
             ws.hdl.barrier(channel=0)
         with _Profiler.span("normalize"):
-            _lib.check(lib.maai_ntxent_normalize_peer(_ptr(h1), _ptr(h2), b, d, dt, _ptr(ws.z_tab[i]), ws.mc_z[i],
-                                                      world, rank, _ptr(inv_norm), _ptr(pos_cos), _ptr(wsp),
-                                                      wsp.numel() * 4, st),
-                       "maai_ntxent_normalize_peer")
+            if chain is not None:  # view-a halves: local copy from the previous set; only view b crosses NVLink
+                _lib.check(lib.maai_ntxent_normalize_chain(_ptr(h2), b, d, dt, _ptr(chain["z_all"]),
+                                                           _ptr(chain["inv_norm"]), _ptr(z_all), _ptr(ws.z_tab[i]),
+                                                           ws.mc_z[i], world, rank, _ptr(inv_norm), _ptr(pos_cos),
+                                                           _ptr(wsp), wsp.numel() * 4, st), "maai_ntxent_normalize_chain")
+            else:
+                _lib.check(lib.maai_ntxent_normalize_peer(_ptr(h1), _ptr(h2), b, d, dt, _ptr(ws.z_tab[i]), ws.mc_z[i],
+                                                          world, rank, _ptr(inv_norm), _ptr(pos_cos), _ptr(wsp),
+                                                          wsp.numel() * 4, st),
+                           "maai_ntxent_normalize_peer")
+        if carry is not None:
+            carry["z_all"], carry["inv_norm"] = z_all, inv_norm
         with _Profiler.span("gather_z"):
             ws.hdl.barrier(channel=0)  # every rank's rows have landed in every buffer
         r_row = r_col = None
@@ -471,7 +490,7 @@ class _NTXentFunction(torch.autograd.Function):
                                                    _ptr(g), b, world, rank, d, dp, inv_tau, need, _ptr(dh1),
                                                    _ptr(dh2), _ptr(dz_acc), flags, _stream(dev)),
                                "maai_ntxent_bwd")
-                out = (dh1, dh2, None, None, None, None, None, None, None)
+                out = (dh1, dh2) + (None,) * 9
         if ctx.peer is not None:
             ws, i = ctx.peer
             ws.backward_issued(i)  # the set's readers are all on the stream now (PeerWorkspace reuse rule)
@@ -504,7 +523,7 @@ def _backward_reduce_scatter(ctx, g, need, dh1, dh2, dz_acc):
         _lib.check(lib.maai_ntxent_bwd_dh(_ptr(dz_acc), _ptr(dz_mine), _ptr(rowsum), _ptr(pos_cos), _ptr(h1),
                                           _ptr(h2), dt, _ptr(inv_norm), _ptr(g), b, d, dp, inv_tau, 1, need,
                                           _ptr(dh1), _ptr(dh2), st), "maai_ntxent_bwd_dh")
-    return dh1, dh2, None, None, None, None, None, None, None
+    return (dh1, dh2) + (None,) * 9
 
 
 _NTXentFunction._backward_reduce_scatter = staticmethod(_backward_reduce_scatter)
@@ -571,7 +590,7 @@ def _warn_once(key: str, msg: str) -> None:
 
 def contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0, local_rank=0, world_size=1,
                      device="cpu", *, group=None, key_grad=None, return_logits=None, fused_topk=False,
-                     peer_gather=None, _stash=None):
+                     peer_gather=None, _stash=None, _chain=None, _carry=None):
     """Drop-in for Objective.contrastive_loss (Objective.py:17-81).
 
     Args (reference): hidden1, hidden2 (bsz, dim); hidden_norm; temperature; local_rank (really the
@@ -633,7 +652,7 @@ def contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0, local_
         else:
             peer = bool(peer_gather)
     loss = _NTXentFunction.apply(hidden1, hidden2, float(temperature), int(local_rank),
-                                 int(world_size), group, key_grad, stash, peer)
+                                 int(world_size), group, key_grad, stash, peer, _chain, _carry)
     logits_ab = labels = None
     if want_logits:
         logits_ab, labels = _logits_and_labels(stash["z_all"], hidden1.shape[0], int(local_rank),
@@ -697,17 +716,50 @@ class GraphedNTXentLoss(torch.nn.Module):
 
 
 class NTXentLoss(torch.nn.Module):
-    """Module form of :func:`contrastive_loss` holding temperature / rank / world / group."""
+    """Module form of :func:`contrastive_loss` holding temperature / rank / world / group.
 
-    def __init__(self, temperature=1.0, local_rank=0, world_size=1, group=None, key_grad=None):
+    ``chain_views=True``: the reference's training loop passes every step's
+    ``outputs2`` to the next step as ``hidden1`` (``outputs1 = outputs2``, Contrastive_Learning.py:700; consumed
+    as ``outputs1.data``, :685).  The module then keeps the previous step's gathered bf16 rows and 1/norms and,
+    when it recognises the chain -- ``hidden1`` is the very tensor memory passed as ``hidden2`` last time,
+    unmodified since, same shape / dtype, not requiring grad -- skips normalising ``hidden1`` and, across
+    ranks, HALF of the embedding gather: the view-a rows of all ranks are copied locally from the previous
+    step's buffer (maai_ntxent_normalize_chain).  Results are identical to the unchained call (the same
+    bf16 rows enter the tile kernels).  Any mismatch (first step, new tensor, in-place update, eval call)
+    silently takes the normal path."""
+
+    def __init__(self, temperature=1.0, local_rank=0, world_size=1, group=None, key_grad=None, chain_views=False,
+                 peer_gather=None):
         super().__init__()
         self.temperature = float(temperature)
         self.local_rank = int(local_rank)
         self.world_size = int(world_size)
         self.group = group
         self.key_grad = key_grad
+        self.chain_views = bool(chain_views)
+        self.peer_gather = peer_gather
+        self._carry = None
+        self.chained_steps = 0  # how many calls took the chained K1 (tests / reporting)
+
+    def _chain_for(self, hidden1):
+        c = self._carry
+        if (c is None or not torch.is_grad_enabled() or hidden1.requires_grad or not hidden1.is_contiguous()
+                or hidden1.data_ptr() != c["h2"].data_ptr() or hidden1.shape != c["h2"].shape
+                or hidden1.dtype != c["h2"].dtype or c["h2"]._version != c["version"]):
+            return None
+        return c
 
     def forward(self, hidden1, hidden2):
-        return contrastive_loss(hidden1, hidden2, True, self.temperature, self.local_rank,
+        chain = self._chain_for(hidden1) if self.chain_views else None
+        carry = {} if (self.chain_views and torch.is_grad_enabled()) else None
+        loss = contrastive_loss(hidden1, hidden2, True, self.temperature, self.local_rank,
                                 self.world_size, hidden1.device, group=self.group,
-                                key_grad=self.key_grad)[0]
+                                key_grad=self.key_grad, peer_gather=self.peer_gather, return_logits=False,
+                                _chain=chain, _carry=carry)[0]
+        if carry:
+            # keeps hidden2's storage alive, so an equal data_ptr next time means the same memory
+            carry["h2"] = hidden2.detach()
+            carry["version"] = hidden2._version
+            self._carry = carry
+            self.chained_steps += chain is not None
+        return loss

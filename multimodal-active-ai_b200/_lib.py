@@ -31,6 +31,9 @@ SIGNATURES = {
                                  _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p]),
     "maai_ntxent_normalize_peer": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
                                             _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "maai_ntxent_normalize_chain": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
+                                             _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
+                                             _c_size_t, _c_void_p]),
     "maai_ntxent_fwd_peer": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p,
                                       _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p]),
     "maai_ntxent_fwd_eval": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p,

@@ -39,7 +39,8 @@ def build(force: bool = False, verbose: bool = False, defs: tuple = (), out: str
     target = out or LIB
     if not force and not out and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defs], "-o", target,
+    tmp = target + ".tmp"  # compile aside, then rename: a concurrent reader (gpurun snapshot) never sees a torn file
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defs], "-o", tmp,
            *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas")
@@ -48,6 +49,7 @@ def build(force: bool = False, verbose: bool = False, defs: tuple = (), out: str
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"nvcc failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
+    os.replace(tmp, target)
     if verbose:
         print(res.stderr)
     return target

@@ -9,6 +9,9 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
 
 #include "../../include/maai_ntxent.h"
 #include "ntxent_aux.cuh"
@@ -69,14 +72,14 @@ int make_rows_tmap(CUtensorMap* m, const void* base, int rows, int d_pad) {
   return MAAI_OK;
 }
 
-// Optional programmatic stream serialization (PDL) for every kernel of the library: with MAAI_PDL=1
-// (and a build with MAAI_PDL_TRIG != 0) the next kernel's launch latency and prologue overlap the tail
-// of the previous one; each kernel calls griddepcontrol.wait before it touches global memory.  Off by
-// default: see the note at MAAI_PDL_TRIG in ptx_sm100.cuh.
+// Programmatic stream serialization (PDL) for every kernel of the library: the next kernel's launch
+// latency and prologue overlap the tail of the previous one; each kernel calls griddepcontrol.wait before it
+// touches global memory (see the rule in ptx_sm100.cuh).  On by default; MAAI_PDL=0 launches without the
+// attribute (plain stream order), for A/B measurements.
 bool pdl_enabled() {
   static const bool on = [] {
     const char* v = getenv("MAAI_PDL");
-    return v && v[0] == '1';
+    return !(v && v[0] == '0');
   }();
   return on;
 }
@@ -238,7 +241,25 @@ int check_common(int b, int world, int rank) {
 
 extern "C" {
 
-int maai_abi_version(void) { return MAAI_ABI_VERSION; }
+// MAAI_DEBUG_SEGV=1: print a native backtrace on SIGSEGV (the Python fault handler shows Python frames only)
+static void segv_handler(int sig) {
+  void* frames[64];
+  const int n = backtrace(frames, 64);
+  const char msg[] = "maai: SIGSEGV, native backtrace:\n";
+  (void)!write(2, msg, sizeof msg - 1);
+  backtrace_symbols_fd(frames, n, 2);
+  signal(sig, SIG_DFL);
+  raise(sig);
+}
+int maai_abi_version(void) {
+  static const bool hooked = [] {
+    const char* v = getenv("MAAI_DEBUG_SEGV");
+    if (v && v[0] == '1') signal(SIGSEGV, segv_handler);
+    return true;
+  }();
+  (void)hooked;
+  return MAAI_ABI_VERSION;
+}
 const char* maai_last_error(void) { return g_err.c_str(); }
 unsigned long long maai_launch_count(void) { return g_launches.load(); }
 
@@ -508,6 +529,50 @@ int maai_ntxent_normalize_peer(const void* h1, const void* h2, int b, int d, int
   if (rc != MAAI_OK) return rc;
   return normalize_impl(h1, h2, b, d, in_dtype, nullptr, peer_z_bases, mc_z_base, world, rank, inv_norm, pos_cos,
                         zero_fill, zero_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int maai_ntxent_normalize_chain(const void* h2, int b, int d, int in_dtype, const void* z_prev,
+                                const float* inv_norm_prev, void* z_new, const void* const* peer_z_bases,
+                                void* mc_z_base, int world, int rank, float* inv_norm, float* pos_cos,
+                                void* zero_fill, size_t zero_bytes, void* stream) {
+  if (!h2 || !z_prev || !inv_norm_prev || !z_new || !inv_norm || !pos_cos) return fail(MAAI_E_ARG, "null pointer");
+  int rc = check_common(b, world, rank);
+  if (rc != MAAI_OK) return rc;
+  const int dp = maai_padded_dim(d);
+  if (dp < 0) return fail(MAAI_E_SHAPE, "embedding dim must be in [1, 256]");
+  if (!aligned16(z_prev) || !aligned16(z_new)) return fail(MAAI_E_ARG, "z_prev and z_new must be 16-byte aligned");
+  if (z_prev == z_new) return fail(MAAI_E_ARG, "z_prev and z_new must be different buffers");
+  if (zero_bytes && (!zero_fill || !aligned16(zero_fill) || (zero_bytes & 3)))
+    return fail(MAAI_E_ARG, "zero_fill must be 16-byte aligned and zero_bytes a multiple of 4");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int wpb = 8;
+  const int grid = (b + wpb - 1) / wpb;
+  const size_t esz = in_dtype == MAAI_DT_F32 ? 4 : 2;
+  const int vec = dp / 32;
+  const bool vec_ok = (d % vec) == 0 && (reinterpret_cast<uintptr_t>(h2) % (vec * esz)) == 0;
+  cudaError_t e = cudaSuccess;
+#define MAAI_K1C(T, V)                                                                                        \
+  e = launch_k(maai::normalize_chain_kernel<T, V>, dim3(grid), dim3(wpb * 32), 0, s, static_cast<const T*>(h2), \
+               b, d, vec_ok, static_cast<const __nv_bfloat16*>(z_prev), inv_norm_prev,                          \
+               static_cast<__nv_bfloat16*>(z_new), reinterpret_cast<const unsigned long long*>(peer_z_bases),   \
+               reinterpret_cast<unsigned long long>(mc_z_base), world, rank, inv_norm, pos_cos,                 \
+               static_cast<uint32_t*>(zero_fill), zero_bytes / 4)
+#define MAAI_K1C_DP(T)               \
+  switch (dp) {                      \
+    case 64: MAAI_K1C(T, 2); break;  \
+    case 128: MAAI_K1C(T, 4); break; \
+    default: MAAI_K1C(T, 8); break;  \
+  }
+  switch (in_dtype) {
+    case MAAI_DT_F32: MAAI_K1C_DP(float); break;
+    case MAAI_DT_BF16: MAAI_K1C_DP(__nv_bfloat16); break;
+    case MAAI_DT_F16: MAAI_K1C_DP(__half); break;
+    default: return fail(MAAI_E_ARG, "in_dtype must be MAAI_DT_F32, MAAI_DT_BF16 or MAAI_DT_F16");
+  }
+#undef MAAI_K1C_DP
+#undef MAAI_K1C
+  MAAI_CUDA(e);
+  return MAAI_OK;
 }
 
 int maai_ntxent_fwd_peer(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,

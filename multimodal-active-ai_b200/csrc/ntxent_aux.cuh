@@ -159,6 +159,73 @@ normalize_cast_kernel(const T* __restrict__ h1, const T* __restrict__ h2, int b,
   }
 }
 
+// K1 for chained views.  The reference's training loop feeds this step's
+// outputs2 to the next step as hidden1 (Contrastive_Learning.py:700 "outputs1 = outputs2", consumed
+// detached at :685), so the view-a rows of EVERY rank at step t are the view-b rows of step t-1, which
+// every rank already holds normalised, in bf16, in its gathered key buffer of step t-1.  This variant
+// therefore reads only hidden2: per pair k it normalises h2[k] -> view-b row (local / multicast / peer
+// stores as in normalize_cast_kernel: half the gather payload), copies the view-b rows k of all `world`
+// slots of the previous buffer into the view-a rows of the new one (a local, L2-resident copy instead of
+// an NVLink transfer) and carries the view-a 1/norm over from the previous step's view b.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+normalize_chain_kernel(const T* __restrict__ h2, int b, int d, bool vec_ok,
+                       const __nv_bfloat16* __restrict__ z_prev, const float* __restrict__ inv_prev,
+                       __nv_bfloat16* __restrict__ z_new, const unsigned long long* __restrict__ peer_base,
+                       unsigned long long mc_base, int world, int rank, float* __restrict__ inv_norm,
+                       float* __restrict__ pos_cos, uint32_t* __restrict__ zero_fill, size_t zero_words) {
+  constexpr int DP = VEC * 32;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  pdl_launch_dependents<1>();
+  pdl_wait();
+  if (zero_words) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    uint4* p4 = reinterpret_cast<uint4*>(zero_fill);
+    for (size_t i = tid; i < zero_words / 4; i += nth) p4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (size_t i = (zero_words / 4) * 4 + tid; i < zero_words; i += nth) zero_fill[i] = 0u;
+  }
+  if (k >= b) return;
+  using Vec = typename std::conditional<VEC == 2, uint32_t, typename std::conditional<VEC == 4, uint2, uint4>::type>::type;
+  float c[VEC];
+  load_row_chunk<T, VEC>(h2 + (size_t)k * d, lane * VEC, d, vec_ok, c);
+  float sc = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) sc += c[i] * c[i];
+  sc = warp_sum(sc);
+  const float ic = 1.f / fmaxf(sqrtf(sc), kNormEps);
+  // view-a rows of every slot <- view-b rows of the previous step's buffer
+  Vec va_own = Vec();
+  for (int q = 0; q < world; ++q) {
+    const Vec v = *reinterpret_cast<const Vec*>(z_prev + ((size_t)q * 2 * b + b + k) * DP + lane * VEC);
+    *reinterpret_cast<Vec*>(z_new + ((size_t)q * 2 * b + k) * DP + lane * VEC) = v;
+    if (q == rank) va_own = v;
+  }
+  __align__(16) __nv_bfloat16 za[VEC], zc[VEC];
+  *reinterpret_cast<Vec*>(za) = va_own;
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    zc[i] = __float2bfloat16_rn(c[i] * ic);
+    dot += __bfloat162float(za[i]) * __bfloat162float(zc[i]);
+  }
+  dot = warp_sum(dot);
+  const Vec vc = *reinterpret_cast<const Vec*>(zc);
+  const size_t off_c = (((size_t)rank * 2 * b + b + k) * DP + lane * VEC) * sizeof(__nv_bfloat16);
+  if (mc_base) {
+    multimem_st(reinterpret_cast<char*>(mc_base) + off_c, vc);
+  } else if (peer_base) {
+    for (int p = 0; p < world; ++p) *reinterpret_cast<Vec*>(reinterpret_cast<char*>(peer_base[p]) + off_c) = vc;
+  } else {
+    *reinterpret_cast<Vec*>(reinterpret_cast<char*>(z_new) + off_c) = vc;
+  }
+  if (lane == 0) {
+    inv_norm[k] = inv_prev[b + k];
+    inv_norm[b + k] = ic;
+    pos_cos[k] = dot;
+  }
+}
+
 // Per-row tail of the forward (Objective.py:76-79): with e_pos = exp((cos_pos - 1)/tau) and l' = sum over
 // the negatives,
 //   lse_i - s_i,pos = ln(e_pos + l'_i) - ln(e_pos) = log1p(l'_i / e_pos)      (Objective.py:76-77)

@@ -15,17 +15,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // ----------------------------------------------------------------------------------------------
 // Programmatic dependent launch (no-ops when the kernel was launched without the attribute)
 // ----------------------------------------------------------------------------------------------
-// Let the next kernel of the stream start launching (its prologue overlaps this kernel's work) ...
-// Which kernels release their dependents early: 1 normalize, 2 zero, 4 tile, 8 finalize, 16 dh.
-// Default 0 = none, and the launch attribute itself is off unless MAAI_PDL=1 (maai_ntxent.cu).
-// Measured with all five triggering: configs[1] (4096 pairs) step 0.142 -> 0.120 ms, but a CUDA-graph
-// replay of two back-to-back steps (tests/test_gpu_parity.py::test_c_abi_is_cuda_graph_capturable)
-// then returns a wrong loss / wrong gradients -- also for subsets in which no persistent tile kernel
-// triggers (bisected with tools/ab_variants.py, profiles/r1_tuning_log.md).  Every kernel waits
-// (griddepcontrol.wait) before its first global access, so the chain should be transitive; until the
-// ordering hole is understood the early triggers stay compiled out.
+// Every kernel of the library is launched with programmatic stream serialization (maai_ntxent.cu,
+// MAAI_PDL=0 turns the attribute off) and, at its top, lets the next kernel of the stream start launching
+// (griddepcontrol.launch_dependents): the dependent's launch latency and prologue (barrier init, TMEM
+// allocation, descriptor prefetch) overlap this kernel's work.  The dependent then blocks in
+// griddepcontrol.wait until this grid has completed and its writes are visible.
+// RULE: every thread of every kernel executes pdl_wait() before its first global access AND before it
+// exits.  A grid whose threads skip the wait can complete before its predecessor has, and the kernel
+// behind it would then see that predecessor's writes unordered: round 1's tile kernel had the trigger
+// but no wait, which is why a CUDA-graph replay of two back-to-back steps returned wrong results with
+// the attribute on (profiles/r1_tuning_log.md); with the wait in place the replay test passes with all
+// five triggers (tests/test_gpu_parity.py::test_c_abi_is_cuda_graph_capturable, profiles/r2_tuning_log.md).
+// Which kernels trigger early (bit mask, build-time for A/B runs): 1 normalize, 2 zero, 4 tile, 8 finalize,
+// 16 dh.
 #ifndef MAAI_PDL_TRIG
-#define MAAI_PDL_TRIG 0
+#define MAAI_PDL_TRIG 31
 #endif
 template <int WHO>
 __device__ __forceinline__ void pdl_launch_dependents() {

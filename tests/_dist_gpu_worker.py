@@ -59,6 +59,99 @@ def main():
             ml = np.mean([res[True][p][0] for p in range(world)])
             print(f"   vs single-process global batch: loss rel {abs(ml - gl) / gl:.2e} dh1 rel {e:.2e}")
             ok = ok and e <= 1e-2 and abs(ml - gl) / gl <= 1e-3
+    # ---- peer workspace reuse (PeerWorkspace docstring): several forwards in flight before their backwards.
+    # Pattern f0 f1 b1 b0 f2 f3 b3 b2 f4 b4 with different inputs per step; every step's gradient must match
+    # the oracle (a rank racing ahead and overwriting a buffer another rank's backward still reads shows up
+    # as a wrong gradient); a third forward in flight must raise instead of overwriting.
+    if peer_gather_available():
+        os.environ["MAAI_FWD_SYM_MULTI"] = "0"
+        b, d, tau = 384, 128, 0.3
+
+        def make(step):
+            g = torch.Generator().manual_seed(1000 + step)
+            H1 = torch.randn(world * b, d, generator=g)
+            H2 = H1 + 0.5 * torch.randn(world * b, d, generator=g)
+            x = H1[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
+            y = H2[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
+            return H1, H2, x, y
+
+        def fwd(step):
+            H1, H2, x, y = make(step)
+            loss = maai_b200.contrastive_loss(x, y, temperature=tau, local_rank=rank, world_size=world, device=dev,
+                                              key_grad=True, peer_gather=True)[0]
+            return dict(H1=H1, H2=H2, x=x, y=y, loss=loss)
+
+        def check(st, tag):
+            nonlocal ok
+            _, o1, o2 = O.contrastive_loss_oracle_distributed(
+                [st["H1"][p * b:(p + 1) * b].numpy() for p in range(world)],
+                [st["H2"][p * b:(p + 1) * b].numpy() for p in range(world)], tau, key_grad=True)
+            e1 = np.linalg.norm(st["x"].grad.cpu().numpy() - o1[rank]) / np.linalg.norm(o1[rank])
+            e2 = np.linalg.norm(st["y"].grad.cpu().numpy() - o2[rank]) / np.linalg.norm(o2[rank])
+            flag = torch.tensor([max(e1, e2)], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print(f"workspace reuse {tag}: max dh rel err over ranks {float(flag):.2e}")
+            ok = ok and float(flag) <= 1e-2
+
+        for rep in range(3):
+            s0, s1 = fwd(10 * rep), fwd(10 * rep + 1)
+            if rank == world - 1:
+                torch.cuda._sleep(20_000_000)   # this rank's backwards run late: the others race ahead
+            s1["loss"].backward(); s0["loss"].backward()
+            s2, s3 = fwd(10 * rep + 2), fwd(10 * rep + 3)
+            s3["loss"].backward(); s2["loss"].backward()
+            for k, st in enumerate((s0, s1, s2, s3)):
+                check(st, f"rep {rep} two-in-flight step {k}")
+        # three in flight: the third forward reuses ... no, takes the third set; the fourth must raise
+        a, b_, c = fwd(100), fwd(101), fwd(102)
+        raised = False
+        try:
+            fwd(103)
+        except RuntimeError as e:
+            raised = "in flight" in str(e)
+        c["loss"].backward(); b_["loss"].backward(); a["loss"].backward()
+        nxt = fwd(104)   # set whose backward was issued after the previous forward: extra barrier path
+        nxt["loss"].backward()
+        for k, st in enumerate((a, b_, c, nxt)):
+            check(st, f"three-in-flight step {k}")
+        if rank == 0:
+            print("fourth forward in flight raised:", raised)
+        ok = ok and raised
+    # ---- chained views across ranks (NTXentLoss(chain_views=True)): half the gather payload, same results
+    for peer in ([False, True] if peer_gather_available() else [False]):
+        b, d, tau = 320, 128, 0.4
+        outs = []
+        for t in range(4):
+            g = torch.Generator().manual_seed(500 + t)
+            outs.append(torch.randn(world * b, d, generator=g))
+        got = {}
+        for chained in (True, False):
+            mod = maai_b200.NTXentLoss(temperature=tau, local_rank=rank, world_size=world, key_grad=True,
+                                       chain_views=chained, peer_gather=peer)
+            o1 = outs[0][rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
+            rows = []
+            for t in range(1, 4):
+                o2 = outs[t][rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
+                loss = mod(o1.data, o2)
+                loss.backward()
+                rows.append((float(loss.detach()), o2.grad.clone()))
+                o1 = o2
+            got[chained] = rows
+            assert mod.chained_steps == (2 if chained else 0), mod.chained_steps
+        worst = 0.0
+        for (lc, gc), (lu, gu) in zip(got[True], got[False]):
+            worst = max(worst, abs(lc - lu) / abs(lu), float((gc - gu).norm() / gu.norm()))
+        # and against the oracle: hidden1 detached, full gradient w.r.t. hidden2
+        _, _, o2f = O.contrastive_loss_oracle_distributed(
+            [outs[2][p * b:(p + 1) * b].numpy() for p in range(world)],
+            [outs[3][p * b:(p + 1) * b].numpy() for p in range(world)], tau, key_grad=True)
+        eo = float(np.linalg.norm(got[True][2][1].cpu().numpy() - o2f[rank]) / np.linalg.norm(o2f[rank]))
+        flag = torch.tensor([worst, eo], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f"chained views peer={peer}: chained vs unchained {float(flag[0]):.2e}, vs oracle dh2 {float(flag[1]):.2e}")
+        ok = ok and float(flag[0]) <= 1e-5 and float(flag[1]) <= 1e-2
     if rank == 0:
         print("DIST_OK" if ok else "DIST_FAIL")
     dist.destroy_process_group()

@@ -34,8 +34,9 @@ def test_native_library_is_loaded():
     before = lib.maai_launch_count()
     _run(np.random.randn(8, 16).astype(np.float32), np.random.randn(8, 16).astype(np.float32), 0.5)
     assert lib.maai_launch_count() - before == 4  # normalise (+ zero fill), fwd tile (+ finalise), bwd tile, dh
+    import os
     maps = open("/proc/self/maps").read()
-    assert "libmaai_ntxent.so" in maps
+    assert os.path.basename(maai_b200._lib.LIB_PATH) in maps  # the in-tree CUDA library is what ran
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -373,3 +374,49 @@ def test_graphed_module_matches_eager(b, d, dtype, grad1):
         assert rel_fro(g2g, o2) <= tol
     with pytest.raises(ValueError):
         fn(torch.zeros(b + 1, d, device=dev, dtype=dtype), torch.zeros(b + 1, d, device=dev, dtype=dtype))
+
+
+@pytest.mark.parametrize("b,d,dtype", [(300, 128, torch.float32), (1000, 64, torch.float32), (257, 200, torch.bfloat16)])
+def test_chained_views_match_unchained(b, d, dtype):
+    """NTXentLoss(chain_views=True) over the reference's loop shape
+    (Contrastive_Learning.py:685-700: hidden1 = outputs1.data, ..., outputs1 = outputs2).  From the second
+    step on, K1 reads only hidden2 and takes the view-a rows from the previous step's buffer; losses and
+    gradients must equal the unchained module's (the same bf16 rows reach the tile kernels) and the oracle's."""
+    import maai_b200
+    from oracle import ntxent_oracle as O
+    tau = 0.3
+    g = torch.Generator().manual_seed(b + d)
+    outs = [torch.randn(b, d, generator=g).to(dtype) for _ in range(5)]
+    res = {}
+    for chained in (True, False):
+        mod = maai_b200.NTXentLoss(temperature=tau, chain_views=chained)
+        outputs1 = outs[0].cuda().requires_grad_(True)
+        rows = []
+        for t in range(1, 5):
+            outputs2 = outs[t].cuda().requires_grad_(True)
+            if t == 3:
+                with torch.no_grad():   # an eval call in between must not disturb the chain state's validity check
+                    mod(outputs1.data, outputs2)
+            loss = mod(outputs1.data, outputs2)
+            loss.backward()
+            rows.append((float(loss.detach()), outputs2.grad.float().cpu().numpy()))
+            outputs1 = outputs2
+        res[chained] = rows
+        assert mod.chained_steps == (3 if chained else 0)
+    for t, ((lc, gc), (lu, gu)) in enumerate(zip(res[True], res[False])):
+        assert abs(lc - lu) <= 1e-6 * abs(lu), t
+        assert rel_fro(gc, gu) <= (1e-5 if dtype == torch.float32 else 4e-3), t
+        ol, _, o2 = O.contrastive_loss_oracle(outs[t].float().numpy(), outs[t + 1].float().numpy(), tau)
+        assert abs(lc - ol) <= LOSS_TOL * abs(ol)
+        assert rel_fro(gc, o2) <= (GRAD_TOL if dtype == torch.float32 else 2e-2)
+    # a broken chain (in-place update of the carried tensor) falls back to the normal K1
+    mod = maai_b200.NTXentLoss(temperature=tau, chain_views=True)
+    a = outs[0].cuda().requires_grad_(True); c = outs[1].cuda().requires_grad_(True)
+    mod(a.data, c).backward()
+    with torch.no_grad():
+        c.mul_(2.0)
+    e = outs[2].cuda().requires_grad_(True)
+    l2 = mod(c.data, e)
+    assert mod.chained_steps == 0
+    ol, _, _ = O.contrastive_loss_oracle(2.0 * outs[1].float().numpy(), outs[2].float().numpy(), tau)
+    assert abs(float(l2) - ol) <= LOSS_TOL * abs(ol)

@@ -17,3 +17,6 @@ python tools/quick_time.py 4096 128 100
 MAAI_PDL=1 MAAI_DEBUG_LIB=$V python tools/quick_time.py 4096 128 100
 } > gpurun_out/r2_run1_timing.log 2>&1
 cat gpurun_out/r2_run1_timing.log
+timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_run1_bench.json 2> gpurun_out/r2_run1_bench.err; echo "bench rc=$?"
+tail -c 3000 gpurun_out/r2_run1_bench.json
+tail -5 gpurun_out/r2_run1_bench.err
