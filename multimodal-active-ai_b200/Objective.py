@@ -651,8 +651,14 @@ def contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0, local_
                                                             int(world_size), int(local_rank), hidden1.device, group)
         else:
             peer = bool(peer_gather)
-    loss = _NTXentFunction.apply(hidden1, hidden2, float(temperature), int(local_rank),
-                                 int(world_size), group, key_grad, stash, peer, _chain, _carry)
+    ext = None
+    if int(world_size) == 1 and stash is None and _carry is None and not _Profiler.enabled:
+        ext = _lib.fast_ext()  # C++ autograd binding of the same C-ABI calls (host cost only)
+    if ext is not None:
+        loss = ext.ntxent_loss(hidden1, hidden2, float(temperature))
+    else:
+        loss = _NTXentFunction.apply(hidden1, hidden2, float(temperature), int(local_rank),
+                                     int(world_size), group, key_grad, stash, peer, _chain, _carry)
     logits_ab = labels = None
     if want_logits:
         logits_ab, labels = _logits_and_labels(stash["z_all"], hidden1.shape[0], int(local_rank),
@@ -701,7 +707,11 @@ class GraphedNTXentLoss(torch.nn.Module):
         self.shape, self.dtype, self.temperature = (int(bsz), int(dim)), dtype, t
         self.requires = (bool(hidden1_requires_grad), bool(hidden2_requires_grad))
 
+        ext = _lib.fast_ext()
+
         def fn(h1, h2):
+            if ext is not None:
+                return ext.ntxent_loss(h1, h2, t)
             return _NTXentFunction.apply(h1, h2, t, 0, 1, None, True, None, False)
         self._graphed = torch.cuda.make_graphed_callables(fn, (a, b))
 

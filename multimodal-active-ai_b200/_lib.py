@@ -59,6 +59,8 @@ SIGNATURES = {
 }
 
 _lib = None
+_ext = None  # False once found missing
+EXT_PATH = os.path.join(HERE, "maai_torch_ext.so")
 
 
 class MaaiError(RuntimeError):
@@ -83,6 +85,27 @@ def load() -> ctypes.CDLL:
         raise MaaiError(f"ABI mismatch: library {lib.maai_abi_version()} != binding {ABI_VERSION}")
     _lib = lib
     return lib
+
+
+def fast_ext():
+    """The C++ autograd binding of the single-rank step (csrc/maai_torch_ext.cpp, built by
+    build.py::build_torch_ext), or None when it has not been built.  It enqueues exactly the C-ABI calls the
+    Python autograd.Function does -- same kernels, same library instance -- at a fraction of the host cost;
+    MAAI_FAST_EXT=0 keeps the Python path (A/B runs).  Never a fallback for the CUDA library itself."""
+    global _ext
+    if _ext is None:
+        _ext = False
+        if os.environ.get("MAAI_FAST_EXT", "1") != "0" and os.path.exists(EXT_PATH):
+            load()  # libmaai_ntxent.so first: the binding links against it (soname match / rpath $ORIGIN)
+            import importlib.util
+            import torch  # noqa: F401  (the binding needs libtorch loaded)
+            spec = importlib.util.spec_from_file_location("maai_torch_ext", EXT_PATH)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            if mod.abi_version() != ABI_VERSION:
+                raise MaaiError(f"maai_torch_ext.so was built against ABI {mod.abi_version()}, binding expects {ABI_VERSION}")
+            _ext = mod
+    return _ext or None
 
 
 def check(rc: int, what: str) -> None:

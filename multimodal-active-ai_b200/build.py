@@ -17,7 +17,7 @@ SOURCES = ["maai_ntxent.cu"]
 DEPS = ["maai_ntxent.cu", "ntxent_tile.cuh", "ntxent_aux.cuh", "ptx_sm100.cuh",
         os.path.join("..", "..", "include", "maai_ntxent.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC", "-Xlinker", "-soname=libmaai_ntxent.so"]
 
 
 def _nvcc() -> str:
@@ -55,5 +55,42 @@ def build(force: bool = False, verbose: bool = False, defs: tuple = (), out: str
     return target
 
 
+EXT_LIB = os.path.join(HERE, "maai_torch_ext.so")
+EXT_SRC = os.path.join(CSRC, "maai_torch_ext.cpp")
+
+
+def ext_needs_build() -> bool:
+    if not os.path.exists(EXT_LIB):
+        return True
+    t = os.path.getmtime(EXT_LIB)
+    return any(os.path.getmtime(f) > t for f in (EXT_SRC, os.path.join(HERE, "..", "include", "maai_ntxent.h")))
+
+
+def build_torch_ext(force: bool = False, verbose: bool = False) -> str:
+    """maai_torch_ext.so: the C++ autograd binding (csrc/maai_torch_ext.cpp), compiled with g++ against the
+    torch headers and linked to the in-tree libmaai_ntxent.so (rpath $ORIGIN).  No CUDA code of its own."""
+    if not force and not ext_needs_build():
+        return EXT_LIB
+    if not os.path.exists(LIB):
+        build()
+    import shutil
+    from torch.utils import cpp_extension
+    bdir = os.path.join(HERE, "build", "torch_ext")
+    os.makedirs(bdir, exist_ok=True)
+    import ctypes
+    ctypes.CDLL(LIB, mode=ctypes.RTLD_GLOBAL)  # so that load()'s trial import of the result resolves its NEEDED entry
+    cpp_extension.load(
+        name="maai_torch_ext", sources=[EXT_SRC], build_directory=bdir, with_cuda=True, verbose=verbose,
+        extra_cflags=["-O2", "-std=c++17"], is_python_module=False,
+        # ninja ($$) and the shell (quotes) both leave $ORIGIN alone: the binding finds the kernels next to it
+        extra_ldflags=[f"-L{HERE}", "-l:libmaai_ntxent.so", "'-Wl,-rpath,$$ORIGIN'"])
+    tmp = EXT_LIB + ".tmp"
+    shutil.copyfile(os.path.join(bdir, "maai_torch_ext.so"), tmp)
+    os.replace(tmp, EXT_LIB)
+    return EXT_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    if "--ext" in sys.argv:
+        print(build_torch_ext(force=True, verbose=True))

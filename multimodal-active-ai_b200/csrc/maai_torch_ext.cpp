@@ -1,0 +1,128 @@
+// C++ autograd binding of the single-rank NT-Xent step (plumbing, not the product: every kernel it
+// enqueues lives in libmaai_ntxent.so behind include/maai_ntxent.h).
+//
+// Why it exists: at the batch sizes the reference trains with (256 - 4096 pairs per GPU,
+// Contrastive_Learning.py:92) the step's kernels take 35 - 85 us while the Python autograd.Function +
+// ctypes path spends ~170 us of host time per step (profiles/r2_tuning_log.md).  The same sequence of C-ABI
+// calls issued from a torch::autograd::Function costs a fraction of that.  multimodal-active-ai_b200/
+// Objective.py routes world_size == 1 training calls here when this module has been built
+// (build.py::build_torch_ext); everything else (multi-rank gathers, evaluation outputs, the reduce-scatter
+// dataflow) stays in Python.  Semantics are identical to _NTXentFunction in Objective.py.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include "../../include/maai_ntxent.h"
+
+namespace {
+
+int dtype_code(const torch::Tensor& t) {
+  switch (t.scalar_type()) {
+    case torch::kFloat32: return MAAI_DT_F32;
+    case torch::kBFloat16: return MAAI_DT_BF16;
+    case torch::kFloat16: return MAAI_DT_F16;
+    default: TORCH_CHECK_TYPE(false, "hidden1/hidden2 must be float32, bfloat16 or float16");
+  }
+  return -1;
+}
+
+void check_rc(int rc, const char* what) {
+  if (rc == MAAI_OK) return;
+  const std::string msg = std::string(what) + ": " + maai_last_error();
+  TORCH_CHECK_VALUE(rc != MAAI_E_ARG && rc != MAAI_E_SHAPE, msg);
+  TORCH_CHECK(false, msg);
+}
+
+struct Layout {  // one fp32 allocation: [step workspace | r_col] (zero-filled by K1) | inv_norm | pos_cos | loss
+  int64_t ws_words, head, r_len, off_r, off_inv, off_cos, off_loss, total;
+};
+Layout make_layout(int b, int dp, bool need_bwd) {
+  Layout l;
+  l.ws_words = (int64_t)(maai_ntxent_workspace_bytes(b, dp, need_bwd ? 1 : 0) / 4);
+  l.head = ((int64_t)2 * b + MAAI_WS_CTL_WORDS + 127) / 128 * 128;
+  l.r_len = need_bwd ? (int64_t)maai_ntxent_r_len(b, 1) : 0;
+  l.off_r = l.ws_words;
+  l.off_inv = (l.off_r + l.r_len + 3) / 4 * 4;
+  l.off_cos = l.off_inv + 2 * b;
+  l.off_loss = l.off_cos + b;
+  l.total = l.off_loss + 4;
+  return l;
+}
+
+class NTXentFn : public torch::autograd::Function<NTXentFn> {
+ public:
+  static torch::Tensor forward(torch::autograd::AutogradContext* ctx, torch::Tensor hidden1, torch::Tensor hidden2,
+                               double temperature) {
+    const auto h1 = hidden1.contiguous();
+    const auto h2 = hidden2.contiguous();
+    const int b = (int)h1.size(0), d = (int)h1.size(1);
+    const int dp = maai_padded_dim(d);
+    TORCH_CHECK_VALUE(dp > 0, "embedding dim ", d, " unsupported: the sm_100a tile kernels take 1 <= d <= 256");
+    const int dt = dtype_code(h1);
+    const float inv_tau = (float)(1.0 / temperature);
+    const bool need_bwd = torch::GradMode::is_enabled() && (hidden1.requires_grad() || hidden2.requires_grad());
+    c10::cuda::CUDAGuard guard(h1.device());
+    void* st = at::cuda::getCurrentCUDAStream(h1.device().index()).stream();
+    const Layout l = make_layout(b, dp, need_bwd);
+    auto z = torch::empty({(int64_t)2 * b, (int64_t)dp}, h1.options().dtype(torch::kBFloat16));
+    auto buf = torch::empty({l.total}, h1.options().dtype(torch::kFloat32));
+    float* base = buf.data_ptr<float>();
+    check_rc(maai_ntxent_normalize(h1.data_ptr(), h2.data_ptr(), b, d, dt, z.data_ptr(), base + l.off_inv,
+                                   base + l.off_cos, base, (size_t)(l.ws_words + l.r_len) * 4, st),
+             "maai_ntxent_normalize");
+    check_rc(maai_ntxent_fwd(z.data_ptr(), b, 1, 0, dp, inv_tau, base + l.off_cos, base,
+                             need_bwd ? base + l.off_r : nullptr, base + l.off_loss, MAAI_F_PREZEROED, st),
+             "maai_ntxent_fwd");
+    if (need_bwd) {
+      ctx->save_for_backward({h1, h2});
+      ctx->saved_data["z"] = z;
+      ctx->saved_data["buf"] = buf;
+      ctx->saved_data["b"] = (int64_t)b;
+      ctx->saved_data["d"] = (int64_t)d;
+      ctx->saved_data["inv_tau"] = (double)inv_tau;
+      ctx->saved_data["clean"] = true;
+    }
+    return buf.narrow(0, l.off_loss, 1).view({});
+  }
+
+  static torch::autograd::variable_list backward(torch::autograd::AutogradContext* ctx,
+                                                 torch::autograd::variable_list grad_out) {
+    const auto saved = ctx->get_saved_variables();
+    const auto& h1 = saved[0];
+    const auto& h2 = saved[1];
+    const auto z = ctx->saved_data["z"].toTensor();
+    const auto buf = ctx->saved_data["buf"].toTensor();
+    const int b = (int)ctx->saved_data["b"].toInt(), d = (int)ctx->saved_data["d"].toInt();
+    const float inv_tau = (float)ctx->saved_data["inv_tau"].toDouble();
+    const bool clean = ctx->saved_data["clean"].toBool();
+    ctx->saved_data["clean"] = false;  // a second backward (retain_graph) zeroes the accumulator itself
+    const int dp = maai_padded_dim(d);
+    const int need = (ctx->needs_input_grad(0) ? 1 : 0) | (ctx->needs_input_grad(1) ? 2 : 0);
+    c10::cuda::CUDAGuard guard(h1.device());
+    void* st = at::cuda::getCurrentCUDAStream(h1.device().index()).stream();
+    const Layout l = make_layout(b, dp, true);
+    float* base = buf.data_ptr<float>();
+    auto g = grad_out[0].to(h1.device(), torch::kFloat32).contiguous();
+    torch::Tensor dh1, dh2;
+    if (need & 1) dh1 = torch::empty_like(h1);
+    if (need & 2) dh2 = torch::empty_like(h2);
+    check_rc(maai_ntxent_bwd(z.data_ptr(), base + l.off_r, base + l.off_r, 1, base, base + l.off_cos, h1.data_ptr(),
+                             h2.data_ptr(), dtype_code(h1), base + l.off_inv, g.data_ptr<float>(), b, 1, 0, d, dp,
+                             inv_tau, need, (need & 1) ? dh1.data_ptr() : nullptr, (need & 2) ? dh2.data_ptr() : nullptr,
+                             base + l.head, clean ? MAAI_F_PREZEROED : 0, st),
+             "maai_ntxent_bwd");
+    return {dh1, dh2, torch::Tensor()};
+  }
+};
+
+torch::Tensor ntxent_loss(torch::Tensor hidden1, torch::Tensor hidden2, double temperature) {
+  return NTXentFn::apply(hidden1, hidden2, temperature);
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "C++ autograd binding of the single-rank NT-Xent step over libmaai_ntxent.so";
+  m.def("ntxent_loss", &ntxent_loss, "loss = NT-Xent(hidden1, hidden2) on one rank (Objective.py:17-81), autograd-aware");
+  m.def("abi_version", [] { return maai_abi_version(); });
+}
