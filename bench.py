@@ -74,9 +74,7 @@ class ClockSampler:
     def _loop(self):
         try:
             import pynvml
-            pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            h = self.handle
             while not self.stop_flag.is_set():
                 sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
                 pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
@@ -85,11 +83,19 @@ class ClockSampler:
                 except Exception:
                     rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 self.samples.append((sm, pw, rs))
-                time.sleep(0.01)
+                time.sleep(0.002)
         except Exception as e:  # noqa: BLE001
             self.err = repr(e)
 
     def start(self):
+        try:  # NVML initialisation takes longer than a 20-step run: do it before the thread starts sampling
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            return
         self.thread = threading.Thread(target=self._loop, daemon=True)
         self.thread.start()
 

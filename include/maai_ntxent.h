@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MAAI_ABI_VERSION 6
+#define MAAI_ABI_VERSION 7
 
 #define MAAI_OK 0
 #define MAAI_E_ARG (-1)
@@ -60,6 +60,29 @@ size_t maai_ntxent_workspace_bytes(int b, int d_pad, int need_bwd);
  * only, by size, MAAI_FWD_SYM=0/1 forces.  Reporting / tests; the result is the same either way. */
 int maai_ntxent_fwd_is_symmetric(int b, int world, int d_pad);
 
+/* In-kernel peer synchronisation (world > 1, optional; NULL = the caller orders the fused gathers with its own
+ * barrier between the calls).  Every rank owns a FLAG BLOCK of MAAI_FLAG_WORDS 32-bit words in peer-mapped
+ * memory, zero before the first step: word [kind*32 + p] = the last step whose stores of that kind rank p has
+ * completed into THIS rank's buffers (kind 0: bf16 rows, 1: row factors, 2: staged partial row sums).  A
+ * producing kernel fences its peer / multicast stores at system scope and its last CTA release-stores `seq`
+ * into its word of every rank's block; a consuming kernel spins (bounded: it traps after ~3 s, it never
+ * hangs) on its LOCAL block with acquire loads right before its TMA producer first touches rows of the
+ * rank in question.  No barrier kernel, no host involvement: K1's stores and the first tiles of the forward
+ * overlap, and the whole multi-rank step is a fixed sequence of this library's kernels.
+ *   peer_flag_bases  DEVICE array of `world` device pointers: rank p's flag block as mapped into this process
+ *   local_flags      this rank's own flag block
+ *   counter          one zero-initialised 32-bit device word of scratch (CTA-done counter, self-resetting)
+ *   seq              step number: > 0, the same on every rank, larger at every step
+ * Buffer reuse stays the caller's business exactly as with barriers: a rank that has observed seq = t from a
+ * peer knows that peer has enqueued, and its GPU executed, everything before its K1 of step t. */
+#define MAAI_FLAG_WORDS 96
+typedef struct maai_peer_sync {
+  const void* const* peer_flag_bases;
+  unsigned int* local_flags;
+  unsigned int* counter;
+  unsigned int seq;
+} maai_peer_sync;
+
 /* Number of floats the `r_glob` array of maai_ntxent_bwd must hold: world*2b rounded up to 128. */
 size_t maai_ntxent_r_len(int b, int world);
 
@@ -89,6 +112,7 @@ int maai_ntxent_normalize(const void* h1, const void* h2, int b, int d, int in_d
  *              runs the per-row tail itself (one launch for the whole forward). */
 int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
                     const float* pos_cos, float* rowsum_l, float* r_out, float* loss_out, int flags,
+                    const maai_peer_sync* sync /* world > 1: wait for the peers' rows in the kernel, or NULL */,
                     void* stream);
 
 /* K1 fused with the cross-replica embedding gather (replaces Objective.py:41-43 AND :52-53, 102-114):
@@ -101,7 +125,9 @@ int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, f
  *                 row is stored ONCE and the NVSwitch replicates it into every rank's buffer */
 int maai_ntxent_normalize_peer(const void* h1, const void* h2, int b, int d, int in_dtype,
                                const void* const* peer_z_bases, void* mc_z_base, int world, int rank,
-                               float* inv_norm, float* pos_cos, void* zero_fill, size_t zero_bytes, void* stream);
+                               float* inv_norm, float* pos_cos, void* zero_fill, size_t zero_bytes,
+                               const maai_peer_sync* sync /* signal kind 0 when the rows have landed, or NULL */,
+                               void* stream);
 
 /* K1 for CHAINED VIEWS: the reference's training loop passes this step's
  * outputs2 to the next step as hidden1 ("outputs1 = outputs2", Contrastive_Learning.py:700; consumed
@@ -117,7 +143,7 @@ int maai_ntxent_normalize_peer(const void* h1, const void* h2, int b, int d, int
 int maai_ntxent_normalize_chain(const void* h2, int b, int d, int in_dtype, const void* z_prev,
                                 const float* inv_norm_prev, void* z_new, const void* const* peer_z_bases,
                                 void* mc_z_base, int world, int rank, float* inv_norm, float* pos_cos,
-                                void* zero_fill, size_t zero_bytes, void* stream);
+                                void* zero_fill, size_t zero_bytes, const maai_peer_sync* sync, void* stream);
 
 /* K2 fused with the all-gather of the row factors: like maai_ntxent_fwd, but r_i is stored into slot
  * `rank` of every rank's gathered r array (maai_ntxent_r_len floats each, zero padded by the owner).
@@ -125,7 +151,9 @@ int maai_ntxent_normalize_chain(const void* h2, int b, int d, int in_dtype, cons
  *   mc_r_base     multicast address of the r arrays, or NULL */
 int maai_ntxent_fwd_peer(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
                          const float* pos_cos, float* rowsum_l, const void* const* peer_r_bases,
-                         void* mc_r_base, float* loss_out, int flags, void* stream);
+                         void* mc_r_base, float* loss_out, int flags,
+                         const maai_peer_sync* sync /* wait kind 0 per key slot, signal kind 1 after the r stores */,
+                         void* stream);
 
 /* K2 across ranks with the symmetry of E (world > 1): E_ij = E_ji, so every (anchor slot, key slot)
  * pair of ranks needs its tiles computed ONCE.  Rank p computes its own block (the tiles on / above the
@@ -139,10 +167,13 @@ int maai_ntxent_fwd_peer(const void* z_glob, int b, int world, int rank, int d_p
  *   stage_bases  device array of `world` addresses: every rank's `stage`, as mapped into this process
  *   r_out        (2b) or NULL;  peer_r_bases / mc_r_base as in maai_ntxent_fwd_peer, or NULL */
 int maai_ntxent_fwd_sym_tiles(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
-                              float* rowsum_l, float* stage, int flags /* MAAI_F_PREZEROED: rowsum_l */, void* stream);
+                              float* rowsum_l, float* stage, int flags /* MAAI_F_PREZEROED: rowsum_l */,
+                              const maai_peer_sync* sync /* wait kind 0 per anchor slot, signal kind 2 at the end */,
+                              void* stream);
 int maai_ntxent_fwd_sym_finalize(float* rowsum_l, const void* const* stage_bases, int b, int world, int rank,
                                  float inv_tau, const float* pos_cos, float* r_out,
                                  const void* const* peer_r_bases, void* mc_r_base, float* loss_out,
+                                 const maai_peer_sync* sync /* wait kind 2 of every peer, signal kind 1 */,
                                  void* stream);
 
 /* K2 for validate() (Contrastive_Learning.py:860-868): the same forward plus, for every view-a anchor
@@ -177,7 +208,9 @@ int maai_ntxent_fwd_eval(const void* z_glob, int b, int world, int rank, int d_p
 int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, int key_grad,
                     const float* rowsum_l, const float* pos_cos, const void* h1, const void* h2, int in_dtype,
                     const float* inv_norm, const float* grad_loss, int b, int world, int rank, int d, int d_pad,
-                    float inv_tau, int need_mask, void* dh1, void* dh2, float* dz_acc, int flags, void* stream);
+                    float inv_tau, int need_mask, void* dh1, void* dh2, float* dz_acc, int flags,
+                    const maai_peer_sync* sync /* wait kind 1 per key slot before its r_col is read, or NULL */,
+                    void* stream);
 
 /* The backward in its three pieces, for the key-side REDUCE-SCATTER dataflow (SURVEY.md section 7 /
  * BASELINE.json north_star): instead of using the symmetry of E (maai_ntxent_bwd, key_grad = 1), every

@@ -23,6 +23,7 @@ Differences from the reference, all deliberate:
 """
 from __future__ import annotations
 
+import ctypes
 import math
 import os
 from typing import Optional
@@ -181,7 +182,9 @@ class PeerWorkspace:
         # this rank computed for the other ranks' anchors (maai_ntxent_fwd_sym_tiles)
         sb = world * 2 * b * 4
         self.off_s = [self.NBUF * (align(zb) + align(rb)) + i * align(sb) for i in range(self.NBUF)]
-        total = self.NBUF * (align(zb) + align(rb) + align(sb))
+        # flag block of the in-kernel peer synchronisation (maai_peer_sync) + one counter word
+        self.off_f = self.NBUF * (align(zb) + align(rb) + align(sb))
+        total = self.off_f + align(_lib.FLAG_WORDS * 4) + 256
         self.raw = symm_mem.empty((total,), dtype=torch.uint8, device=device)
         self.raw.zero_()                                 # r padding must read as zero
         self.hdl = symm_mem.rendezvous(self.raw, group if group is not None else dist.group.WORLD)
@@ -191,6 +194,12 @@ class PeerWorkspace:
         self.r_tab = [tab(o) for o in self.off_r]
         self.s_tab = [tab(o) for o in self.off_s]
         self.stage = [self.raw[o:o + sb].view(torch.float32) for o in self.off_s]
+        self.f_tab = tab(self.off_f)
+        self.flags = self.raw[self.off_f:self.off_f + _lib.FLAG_WORDS * 4].view(torch.int32)
+        self.counter = self.raw[self.off_f + align(_lib.FLAG_WORDS * 4):][:4].view(torch.int32)
+        # MAAI_PEER_FLAGS=0: order the fused gathers with symmetric-memory barrier launches instead (A/B runs)
+        self.use_flags = os.environ.get("MAAI_PEER_FLAGS", "1") != "0"
+        self.seq = 0
         self.z = [self.raw[o:o + zb].view(torch.bfloat16).view(world, 2 * b, dp) for o in self.off_z]
         self.r = [self.raw[o:o + rb].view(torch.float32) for o in self.off_r]
         # NVSwitch multicast mapping of the same allocation (one store reaches every rank), if the
@@ -240,6 +249,12 @@ class PeerWorkspace:
         self.bwd_pending[i] = bool(needs_bwd)
         self.bwd_stamp[i] = -1
         return i, extra
+
+    def sync_for(self, seq: int):
+        """maai_peer_sync for step `seq` (None when barrier launches are used instead)."""
+        if not self.use_flags:
+            return None
+        return _lib.PeerSync(self.f_tab.data_ptr(), self.flags.data_ptr(), self.counter.data_ptr(), seq)
 
     def backward_issued(self, i: int):
         self.bwd_pending[i] = False
@@ -357,7 +372,7 @@ class _NTXentFunction(torch.autograd.Function):
                     _lib.check(lib.maai_ntxent_normalize_chain(_ptr(h2), b, d, dt, _ptr(chain["z_all"]),
                                                                _ptr(chain["inv_norm"]), _ptr(z_all), None, None, world,
                                                                rank, _ptr(inv_norm), _ptr(pos_cos), _ptr(ws),
-                                                               ws.numel() * 4, st), "maai_ntxent_normalize_chain")
+                                                               ws.numel() * 4, None, st), "maai_ntxent_normalize_chain")
                 else:
                     _lib.check(lib.maai_ntxent_normalize(_ptr(h1), _ptr(h2), b, d, dt, _ptr(z_all[rank]),
                                                          _ptr(inv_norm), _ptr(pos_cos), _ptr(ws), ws.numel() * 4, st),
@@ -368,7 +383,7 @@ class _NTXentFunction(torch.autograd.Function):
                 gather_rows(z_all, rank, group)
             with _Profiler.span("fwd"):
                 _lib.check(lib.maai_ntxent_fwd(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(pos_cos),
-                                               _ptr(rowsum), _ptr(r_row), _ptr(loss), _lib.F_PREZEROED, st),
+                                               _ptr(rowsum), _ptr(r_row), _ptr(loss), _lib.F_PREZEROED, None, st),
                            "maai_ntxent_fwd")
             if needs_grad:
                 if full:
@@ -387,7 +402,9 @@ class _NTXentFunction(torch.autograd.Function):
 
     @staticmethod
     def _forward_peer(ctx, h1, h2, dt, inv_tau, rank, world, group, needs_grad, full, stash, chain=None, carry=None):
-        """world > 1 with the gathers fused into the producing kernels (PeerWorkspace)."""
+        """world > 1 with the gathers fused into the producing kernels (PeerWorkspace).  Ordering across ranks:
+        in-kernel flags (maai_peer_sync: the producers signal, the consumers' TMA producers wait, no barrier
+        launch) or, with MAAI_PEER_FLAGS=0, symmetric-memory barrier launches between the calls."""
         lib = _lib.load()
         b, d = h1.shape
         dev = h1.device
@@ -395,6 +412,9 @@ class _NTXentFunction(torch.autograd.Function):
         st = _stream(dev)
         ws = PeerWorkspace.get(b, dp, world, rank, dev, group)
         i, extra_barrier = ws.next_set(needs_grad)
+        ws.seq += 1
+        sync = ws.sync_for(ws.seq)   # ctypes struct (kept alive until the calls below have returned) or None
+        psync = ctypes.byref(sync) if sync is not None else None
         z_all = ws.z[i]
         wsp, rowsum, dz_acc = _step_workspace(lib, b, dp, needs_grad, dev)
         small = torch.empty(3 * b + 4, dtype=torch.float32, device=dev)
@@ -408,16 +428,18 @@ class _NTXentFunction(torch.autograd.Function):
                 _lib.check(lib.maai_ntxent_normalize_chain(_ptr(h2), b, d, dt, _ptr(chain["z_all"]),
                                                            _ptr(chain["inv_norm"]), _ptr(z_all), _ptr(ws.z_tab[i]),
                                                            ws.mc_z[i], world, rank, _ptr(inv_norm), _ptr(pos_cos),
-                                                           _ptr(wsp), wsp.numel() * 4, st), "maai_ntxent_normalize_chain")
+                                                           _ptr(wsp), wsp.numel() * 4, psync, st),
+                           "maai_ntxent_normalize_chain")
             else:
                 _lib.check(lib.maai_ntxent_normalize_peer(_ptr(h1), _ptr(h2), b, d, dt, _ptr(ws.z_tab[i]), ws.mc_z[i],
                                                           world, rank, _ptr(inv_norm), _ptr(pos_cos), _ptr(wsp),
-                                                          wsp.numel() * 4, st),
+                                                          wsp.numel() * 4, psync, st),
                            "maai_ntxent_normalize_peer")
         if carry is not None:
             carry["z_all"], carry["inv_norm"] = z_all, inv_norm
-        with _Profiler.span("gather_z"):
-            ws.hdl.barrier(channel=0)  # every rank's rows have landed in every buffer
+        if sync is None:
+            with _Profiler.span("gather_z"):
+                ws.hdl.barrier(channel=0)  # every rank's rows have landed in every buffer
         r_row = r_col = None
         peer_r = needs_grad and full
         if not peer_r and needs_grad:  # keys detached (reference semantics): local row factors only, r_col = 0
@@ -426,39 +448,41 @@ class _NTXentFunction(torch.autograd.Function):
         if _sym_forward_enabled(b, dp, world):
             # every pair of rank slots is computed once: own block + the anchors of the ranks ahead on
             # the ring against the local keys; the other half of each row sum arrives through the
-            # peers' staging vectors after a barrier
+            # peers' staging vectors (after a barrier, or once their flags say so)
             with _Profiler.span("fwd"):
                 _lib.check(lib.maai_ntxent_fwd_sym_tiles(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(rowsum),
-                                                         _ptr(ws.stage[i]), _lib.F_PREZEROED, st),
+                                                         _ptr(ws.stage[i]), _lib.F_PREZEROED, psync, st),
                            "maai_ntxent_fwd_sym_tiles")
-            with _Profiler.span("gather_l"):
-                ws.hdl.barrier(channel=2)
+            if sync is None:
+                with _Profiler.span("gather_l"):
+                    ws.hdl.barrier(channel=2)
             with _Profiler.span("finalize"):
                 _lib.check(lib.maai_ntxent_fwd_sym_finalize(_ptr(rowsum), _ptr(ws.s_tab[i]), b, world, rank, inv_tau,
                                                             _ptr(pos_cos), _ptr(r_row),
                                                             _ptr(ws.r_tab[i]) if peer_r else None,
-                                                            ws.mc_r[i] if peer_r else None, _ptr(loss), st),
+                                                            ws.mc_r[i] if peer_r else None, _ptr(loss), psync, st),
                            "maai_ntxent_fwd_sym_finalize")
         else:
             with _Profiler.span("fwd"):
                 if peer_r:
                     _lib.check(lib.maai_ntxent_fwd_peer(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(pos_cos),
                                                         _ptr(rowsum), _ptr(ws.r_tab[i]), ws.mc_r[i], _ptr(loss),
-                                                        _lib.F_PREZEROED, st),
+                                                        _lib.F_PREZEROED, psync, st),
                                "maai_ntxent_fwd_peer")
                 else:
                     _lib.check(lib.maai_ntxent_fwd(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(pos_cos),
-                                                   _ptr(rowsum), _ptr(r_row), _ptr(loss), _lib.F_PREZEROED, st),
+                                                   _ptr(rowsum), _ptr(r_row), _ptr(loss), _lib.F_PREZEROED, psync, st),
                                "maai_ntxent_fwd")
         if needs_grad:
             if full:
-                with _Profiler.span("gather_r"):
-                    ws.hdl.barrier(channel=1)  # every rank's row factors have landed everywhere
+                if sync is None:
+                    with _Profiler.span("gather_r"):
+                        ws.hdl.barrier(channel=1)  # every rank's row factors have landed everywhere
                 r_col = ws.r[i]
                 r_row = r_col[rank * 2 * b:(rank + 1) * 2 * b]
             ctx.save_for_backward(h1, h2, z_all, inv_norm, r_row, r_col, pos_cos, rowsum)
             ctx.cfg = (b, d, dp, dt, inv_tau, rank, world, full)
-            ctx.peer = (ws, i)
+            ctx.peer = (ws, i, ws.seq if (sync is not None and full) else 0)
             ctx.dz_acc = dz_acc
             ctx.acc_clean = True
         if stash is not None:
@@ -480,6 +504,10 @@ class _NTXentFunction(torch.autograd.Function):
         dz_acc = ctx.dz_acc
         flags = _lib.F_PREZEROED if ctx.acc_clean else 0
         ctx.acc_clean = False
+        psync = None
+        if ctx.peer is not None and ctx.peer[2]:  # the peers' row factors: waited for inside the kernel
+            sync = ctx.peer[0].sync_for(ctx.peer[2])
+            psync = ctypes.byref(sync)
         with _on_device(dev):
             if ctx.rs:
                 out = _NTXentFunction._backward_reduce_scatter(ctx, g, need, dh1, dh2, dz_acc)
@@ -488,12 +516,11 @@ class _NTXentFunction(torch.autograd.Function):
                     _lib.check(lib.maai_ntxent_bwd(_ptr(z_all), _ptr(r_row), _ptr(r_col), 1 if full else 0,
                                                    _ptr(rowsum), _ptr(pos_cos), _ptr(h1), _ptr(h2), dt, _ptr(inv_norm),
                                                    _ptr(g), b, world, rank, d, dp, inv_tau, need, _ptr(dh1),
-                                                   _ptr(dh2), _ptr(dz_acc), flags, _stream(dev)),
+                                                   _ptr(dh2), _ptr(dz_acc), flags, psync, _stream(dev)),
                                "maai_ntxent_bwd")
                 out = (dh1, dh2) + (None,) * 9
         if ctx.peer is not None:
-            ws, i = ctx.peer
-            ws.backward_issued(i)  # the set's readers are all on the stream now (PeerWorkspace reuse rule)
+            ctx.peer[0].backward_issued(ctx.peer[1])  # the set's readers are all on the stream now (PeerWorkspace reuse rule)
         return out
 
 

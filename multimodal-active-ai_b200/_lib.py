@@ -9,13 +9,23 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # MAAI_DEBUG_LIB selects an A/B build of the same library (tools/ab_variants.py); never a fallback
 LIB_PATH = os.environ.get("MAAI_DEBUG_LIB") or os.path.join(HERE, "libmaai_ntxent.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 F_PREZEROED = 1
 WS_CTL_WORDS = 32
 OK, E_ARG, E_SHAPE, E_CUDA = 0, -1, -2, -3
 DT_F32, DT_BF16, DT_F16 = 0, 1, 2
 
 _c_int, _c_float, _c_void_p, _c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+FLAG_WORDS = 96
+
+
+class PeerSync(ctypes.Structure):
+    """maai_peer_sync of include/maai_ntxent.h (host struct handed to the calls by pointer)."""
+    _fields_ = [("peer_flag_bases", _c_void_p), ("local_flags", _c_void_p), ("counter", _c_void_p),
+                ("seq", ctypes.c_uint)]
+
+
+_c_sync_p = ctypes.POINTER(PeerSync)
 
 # name -> (restype, argtypes): every symbol declared in include/maai_ntxent.h
 SIGNATURES = {
@@ -28,23 +38,24 @@ SIGNATURES = {
     "maai_ntxent_normalize": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p,
                                        _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "maai_ntxent_fwd": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p,
-                                 _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p]),
+                                 _c_void_p, _c_void_p, _c_void_p, _c_int, _c_sync_p, _c_void_p]),
     "maai_ntxent_normalize_peer": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
-                                            _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+                                            _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_size_t, _c_sync_p,
+                                            _c_void_p]),
     "maai_ntxent_normalize_chain": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
                                              _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
-                                             _c_size_t, _c_void_p]),
+                                             _c_size_t, _c_sync_p, _c_void_p]),
     "maai_ntxent_fwd_peer": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p,
-                                      _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p]),
+                                      _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_sync_p, _c_void_p]),
     "maai_ntxent_fwd_eval": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p,
                                       _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "maai_ntxent_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                  _c_int, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int,
-                                 _c_float, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p]),
+                                 _c_float, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_sync_p, _c_void_p]),
     "maai_ntxent_fwd_sym_tiles": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p,
-                                           _c_int, _c_void_p]),
+                                           _c_int, _c_sync_p, _c_void_p]),
     "maai_ntxent_fwd_sym_finalize": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p,
-                                              _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
+                                              _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_sync_p, _c_void_p]),
     "maai_ntxent_bwd_tiles": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float,
                                        _c_int, _c_void_p, _c_void_p]),
     "maai_ntxent_bwd_keyside": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float,

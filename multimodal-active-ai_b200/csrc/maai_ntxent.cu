@@ -140,6 +140,27 @@ cudaError_t ensure_smem_attr(K kernel, int bytes, std::atomic<unsigned long long
   return e;
 }
 
+// include/maai_ntxent.h maai_peer_sync (host struct, may be null) -> the device-side view
+maai::PeerSync to_sync(const maai_peer_sync* sy, int world, int rank) {
+  maai::PeerSync s{};
+  if (sy && sy->peer_flag_bases) {
+    s.peer_flags = reinterpret_cast<const unsigned long long*>(sy->peer_flag_bases);
+    s.local_flags = sy->local_flags;
+    s.counter = sy->counter;
+    s.seq = sy->seq;
+    s.world = world;
+    s.rank = rank;
+  }
+  return s;
+}
+int check_sync(const maai_peer_sync* sy, int world) {
+  if (!sy) return MAAI_OK;
+  if (!sy->peer_flag_bases || !sy->local_flags || !sy->counter) return fail(MAAI_E_ARG, "maai_peer_sync: null pointer");
+  if (sy->seq == 0) return fail(MAAI_E_ARG, "maai_peer_sync: seq must be > 0");
+  if (world > maai::kFlagStride) return fail(MAAI_E_SHAPE, "maai_peer_sync: world must be <= 32");
+  return MAAI_OK;
+}
+
 struct RankArgs {
   const float* pos_cos = nullptr;
   int* rank_out = nullptr;
@@ -148,6 +169,10 @@ struct RankArgs {
   // forward: in-kernel finalize by the last CTA (null done_ctr = separate finalize launch)
   unsigned int* done_ctr = nullptr;
   maai::FinalizeArgs fin = {};
+  // multi-rank: producer-side waits on the peers' flags (null = ordered by the caller's barrier)
+  const unsigned int* wait_flags = nullptr;
+  unsigned int wait_seq = 0;
+  int wait_kind = 0, wait_slot_rows = 1, wait_my_slot = 0;
 };
 
 template <int D, bool BWD, int NQ, bool RANK = false, bool SYM = false>
@@ -165,6 +190,12 @@ int launch_tile(const void* q_base, int m_loc, const void* k_base, int m_glob, i
   maai::TileParams p{};
   p.done_ctr = ra.done_ctr;
   p.fin = ra.fin;
+  p.wait_flags = ra.wait_flags;
+  p.wait_seq = ra.wait_seq;
+  p.wait_kind = ra.wait_kind;
+  p.wait_what = ra.wait_flags ? 1 : 0;
+  p.wait_slot_rows = ra.wait_slot_rows;
+  p.wait_my_slot = ra.wait_my_slot;
   p.m_loc = m_loc;
   p.m_glob = m_glob;
   p.row_global_base = row_global_base;
@@ -294,8 +325,11 @@ int maai_ntxent_fwd_is_symmetric(int b, int world, int d_pad) {
 // K1 in all its forms: local slot and / or peer / multicast stores, optional zero fill
 static int normalize_impl(const void* h1, const void* h2, int b, int d, int in_dtype, void* z_local,
                           const void* const* peer_z_bases, void* mc_z_base, int world, int rank, float* inv_norm,
-                          float* pos_cos, void* zero_fill, size_t zero_bytes, cudaStream_t s) {
+                          float* pos_cos, void* zero_fill, size_t zero_bytes, cudaStream_t s,
+                          const maai_peer_sync* sync = nullptr) {
   if (!h1 || !h2 || !inv_norm || !pos_cos) return fail(MAAI_E_ARG, "null pointer");
+  if (check_sync(sync, world) != MAAI_OK) return MAAI_E_ARG;
+  const maai::PeerSync dsync = to_sync(sync, world, rank);
   if (b < 1) return fail(MAAI_E_ARG, "b must be >= 1");
   const int dp = maai_padded_dim(d);
   if (dp < 0) return fail(MAAI_E_SHAPE, "embedding dim must be in [1, 256]");
@@ -315,7 +349,7 @@ static int normalize_impl(const void* h1, const void* h2, int b, int d, int in_d
   e = launch_k(maai::normalize_cast_kernel<T, V>, dim3(grid), dim3(wpb * 32), 0, s, static_cast<const T*>(h1), \
                static_cast<const T*>(h2), b, d, vec_ok, static_cast<__nv_bfloat16*>(z_local), pb,              \
                reinterpret_cast<unsigned long long>(mc_z_base), world, rank, inv_norm, pos_cos,                 \
-               static_cast<uint32_t*>(zero_fill), zero_bytes / 4)
+               static_cast<uint32_t*>(zero_fill), zero_bytes / 4, dsync)
 #define MAAI_K1_DP(T)               \
   switch (dp) {                     \
     case 64: MAAI_K1(T, 2); break;  \
@@ -343,8 +377,10 @@ int maai_ntxent_normalize(const void* h1, const void* h2, int b, int d, int in_d
 
 static maai::FinalizeArgs make_fin(float* rowsum_l, const float* pos_cos, int b, float inv_tau, float* r_out,
                                    float* loss_out, const void* const* peer_r, int world, int rank, void* mc_r,
-                                   const void* const* stage_bases) {
-  maai::FinalizeArgs f;
+                                   const void* const* stage_bases, const maai_peer_sync* sync = nullptr) {
+  maai::FinalizeArgs f{};
+  // flags only matter when something crosses ranks here: row factors out (peer_r) or staged sums in
+  if (sync && (peer_r || mc_r || stage_bases)) f.sync = to_sync(sync, world, rank);
   f.l = rowsum_l;
   f.pos_cos = pos_cos;
   f.b = b;
@@ -370,8 +406,9 @@ static int tail_finalize_rows() {
 static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
                     const float* pos_cos, float* rowsum_l, float* r_out, float* loss_out,
                     int* pos_rank, int flags, void* stream, const void* const* peer_r = nullptr,
-                    void* mc_r = nullptr) {
+                    void* mc_r = nullptr, const maai_peer_sync* sync = nullptr) {
   if (!z_glob || !pos_cos || !rowsum_l || !loss_out) return fail(MAAI_E_ARG, "null pointer");
+  if (check_sync(sync, world) != MAAI_OK) return MAAI_E_ARG;
   int rc = check_common(b, world, rank);
   if (rc != MAAI_OK) return rc;
   if (!(inv_tau > 0.f)) return fail(MAAI_E_ARG, "temperature must be positive");
@@ -383,8 +420,15 @@ static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, f
   if (!prezeroed && (rc = zero_words(rowsum_l, (size_t)m_loc, s)) != MAAI_OK) return rc;
   const char* q_base = static_cast<const char*>(z_glob) + (size_t)rank * m_loc * d_pad * 2;
   const maai::FinalizeArgs fin =
-      make_fin(rowsum_l, pos_cos, b, inv_tau, r_out, loss_out, peer_r, world, rank, mc_r, nullptr);
+      make_fin(rowsum_l, pos_cos, b, inv_tau, r_out, loss_out, peer_r, world, rank, mc_r, nullptr, sync);
   RankArgs ra;
+  if (sync && world > 1) {  // key tiles of the other ranks' slots: wait for their rows in the kernel
+    ra.wait_flags = sync->local_flags;
+    ra.wait_seq = sync->seq;
+    ra.wait_kind = maai::FLAG_Z;
+    ra.wait_slot_rows = m_loc;
+    ra.wait_my_slot = rank;
+  }
   const bool tail = prezeroed && !pos_rank && m_loc <= tail_finalize_rows();
   if (tail) {
     ra.done_ctr = reinterpret_cast<unsigned int*>(rowsum_l + m_loc);  // control word 0 of the workspace
@@ -469,7 +513,7 @@ static GroupPlan plan_groups(int b, int world, int rank, int rb_rows, int nq) {
 
 template <int D, int NQ>
 static int launch_tile_groups(const void* z_glob, int b, int world, int rank, float inv_tau, float* rowsum_l,
-                              float* stage, cudaStream_t s) {
+                              float* stage, cudaStream_t s, const maai_peer_sync* sync) {
   using C = maai::TileCfg<D, false, NQ>;
   static std::atomic<unsigned long long> attr_done{0};
   cudaError_t attr_err =
@@ -504,6 +548,15 @@ static int launch_tile_groups(const void* z_glob, int b, int world, int rank, fl
   }
   p.ngroups = gp.ng;
   p.total_items = gp.total;
+  if (sync) {  // anchor tiles of the groups come from other ranks' slots; the staged sums are announced (FLAG_L)
+    p.wait_flags = sync->local_flags;
+    p.wait_seq = sync->seq;
+    p.wait_kind = maai::FLAG_Z;
+    p.wait_what = 2;
+    p.wait_slot_rows = m_loc;
+    p.wait_my_slot = rank;
+    p.grp_sync = to_sync(sync, world, rank);
+  }
   const long long total = gp.total;
   int sms = sm_count();
   if (sms <= 0) return fail(MAAI_E_CUDA, "no CUDA device");
@@ -516,25 +569,28 @@ static int launch_tile_groups(const void* z_glob, int b, int world, int rank, fl
 
 int maai_ntxent_fwd(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
                     const float* pos_cos, float* rowsum_l, float* r_out, float* loss_out, int flags,
-                    void* stream) {
+                    const maai_peer_sync* sync, void* stream) {
   return fwd_impl(z_glob, b, world, rank, d_pad, inv_tau, pos_cos, rowsum_l, r_out, loss_out, nullptr, flags,
-                  stream);
+                  stream, nullptr, nullptr, sync);
 }
 
 int maai_ntxent_normalize_peer(const void* h1, const void* h2, int b, int d, int in_dtype,
                                const void* const* peer_z_bases, void* mc_z_base, int world, int rank,
-                               float* inv_norm, float* pos_cos, void* zero_fill, size_t zero_bytes, void* stream) {
+                               float* inv_norm, float* pos_cos, void* zero_fill, size_t zero_bytes,
+                               const maai_peer_sync* sync, void* stream) {
   if (!peer_z_bases) return fail(MAAI_E_ARG, "null pointer");
   int rc = check_common(b, world, rank);
   if (rc != MAAI_OK) return rc;
   return normalize_impl(h1, h2, b, d, in_dtype, nullptr, peer_z_bases, mc_z_base, world, rank, inv_norm, pos_cos,
-                        zero_fill, zero_bytes, static_cast<cudaStream_t>(stream));
+                        zero_fill, zero_bytes, static_cast<cudaStream_t>(stream), sync);
 }
 
 int maai_ntxent_normalize_chain(const void* h2, int b, int d, int in_dtype, const void* z_prev,
                                 const float* inv_norm_prev, void* z_new, const void* const* peer_z_bases,
                                 void* mc_z_base, int world, int rank, float* inv_norm, float* pos_cos,
-                                void* zero_fill, size_t zero_bytes, void* stream) {
+                                void* zero_fill, size_t zero_bytes, const maai_peer_sync* sync, void* stream) {
+  if (check_sync(sync, world) != MAAI_OK) return MAAI_E_ARG;
+  const maai::PeerSync dsync = to_sync(sync, world, rank);
   if (!h2 || !z_prev || !inv_norm_prev || !z_new || !inv_norm || !pos_cos) return fail(MAAI_E_ARG, "null pointer");
   int rc = check_common(b, world, rank);
   if (rc != MAAI_OK) return rc;
@@ -556,7 +612,7 @@ int maai_ntxent_normalize_chain(const void* h2, int b, int d, int in_dtype, cons
                b, d, vec_ok, static_cast<const __nv_bfloat16*>(z_prev), inv_norm_prev,                          \
                static_cast<__nv_bfloat16*>(z_new), reinterpret_cast<const unsigned long long*>(peer_z_bases),   \
                reinterpret_cast<unsigned long long>(mc_z_base), world, rank, inv_norm, pos_cos,                 \
-               static_cast<uint32_t*>(zero_fill), zero_bytes / 4)
+               static_cast<uint32_t*>(zero_fill), zero_bytes / 4, dsync)
 #define MAAI_K1C_DP(T)               \
   switch (dp) {                      \
     case 64: MAAI_K1C(T, 2); break;  \
@@ -577,15 +633,16 @@ int maai_ntxent_normalize_chain(const void* h2, int b, int d, int in_dtype, cons
 
 int maai_ntxent_fwd_peer(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
                          const float* pos_cos, float* rowsum_l, const void* const* peer_r_bases,
-                         void* mc_r_base, float* loss_out, int flags, void* stream) {
+                         void* mc_r_base, float* loss_out, int flags, const maai_peer_sync* sync, void* stream) {
   if (!peer_r_bases) return fail(MAAI_E_ARG, "null pointer");
   return fwd_impl(z_glob, b, world, rank, d_pad, inv_tau, pos_cos, rowsum_l, nullptr, loss_out, nullptr, flags,
-                  stream, peer_r_bases, mc_r_base);
+                  stream, peer_r_bases, mc_r_base, sync);
 }
 
 int maai_ntxent_fwd_sym_tiles(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
-                              float* rowsum_l, float* stage, int flags, void* stream) {
+                              float* rowsum_l, float* stage, int flags, const maai_peer_sync* sync, void* stream) {
   if (flags & ~MAAI_F_PREZEROED) return fail(MAAI_E_ARG, "unknown flag");
+  if (check_sync(sync, world) != MAAI_OK) return MAAI_E_ARG;
   if (!z_glob || !rowsum_l || !stage) return fail(MAAI_E_ARG, "null pointer");
   int rc = check_common(b, world, rank);
   if (rc != MAAI_OK) return rc;
@@ -596,9 +653,9 @@ int maai_ntxent_fwd_sym_tiles(const void* z_glob, int b, int world, int rank, in
   if (!(flags & MAAI_F_PREZEROED) && (rc = zero_words(rowsum_l, (size_t)2 * b, s)) != MAAI_OK) return rc;
   if ((rc = zero_words(stage, (size_t)2 * b * world, s)) != MAAI_OK) return rc;
   switch (d_pad) {
-    case 64: return launch_tile_groups<64, 2>(z_glob, b, world, rank, inv_tau, rowsum_l, stage, s);
-    case 128: return launch_tile_groups<128, 2>(z_glob, b, world, rank, inv_tau, rowsum_l, stage, s);
-    case 256: return launch_tile_groups<256, 1>(z_glob, b, world, rank, inv_tau, rowsum_l, stage, s);
+    case 64: return launch_tile_groups<64, 2>(z_glob, b, world, rank, inv_tau, rowsum_l, stage, s, sync);
+    case 128: return launch_tile_groups<128, 2>(z_glob, b, world, rank, inv_tau, rowsum_l, stage, s, sync);
+    case 256: return launch_tile_groups<256, 1>(z_glob, b, world, rank, inv_tau, rowsum_l, stage, s, sync);
     default: return fail(MAAI_E_SHAPE, "d_pad must be 64, 128 or 256");
   }
 }
@@ -632,15 +689,16 @@ int maai_debug_tri_locate(long long idx, int n_key_tiles, int n_row_blocks, int 
 int maai_ntxent_fwd_sym_finalize(float* rowsum_l, const void* const* stage_bases, int b, int world, int rank,
                                  float inv_tau, const float* pos_cos, float* r_out,
                                  const void* const* peer_r_bases, void* mc_r_base, float* loss_out,
-                                 void* stream) {
+                                 const maai_peer_sync* sync, void* stream) {
   if (!rowsum_l || !stage_bases || !pos_cos || !loss_out) return fail(MAAI_E_ARG, "null pointer");
+  if (check_sync(sync, world) != MAAI_OK) return MAAI_E_ARG;
   int rc = check_common(b, world, rank);
   if (rc != MAAI_OK) return rc;
   if (!(inv_tau > 0.f)) return fail(MAAI_E_ARG, "temperature must be positive");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   MAAI_CUDA(launch_k(maai::finalize_loss_kernel, dim3(maai::kFinalizeCluster), dim3(1024), 0, s,
                      make_fin(rowsum_l, pos_cos, b, inv_tau, r_out, loss_out, peer_r_bases, world, rank, mc_r_base,
-                              stage_bases)));
+                              stage_bases, sync)));
   return MAAI_OK;
 }
 
@@ -655,7 +713,7 @@ int maai_ntxent_fwd_eval(const void* z_glob, int b, int world, int rank, int d_p
 // tile pass of the backward over this rank's anchors: zeroes the accumulator rows, then K3
 static int bwd_tiles_impl(const void* z_glob, const float* r_row, const float* r_col, int b, int world, int rank,
                           int d_pad, float inv_tau, int need_mask, float* dz_acc, cudaStream_t s,
-                          bool prezeroed = false) {
+                          bool prezeroed = false, const maai_peer_sync* sync = nullptr) {
   const int m_loc = 2 * b, m_glob = 2 * b * world;
   // anchor rows that need a gradient: both views, or one contiguous view
   const int row_begin = (need_mask == 2) ? b : 0;
@@ -665,8 +723,16 @@ static int bwd_tiles_impl(const void* z_glob, const float* r_row, const float* r
   if (!prezeroed && (rc = zero_words(acc, (size_t)rows * d_pad, s)) != MAAI_OK) return rc;
   const char* q_base =
       static_cast<const char*>(z_glob) + ((size_t)rank * m_loc + row_begin) * d_pad * 2;
+  RankArgs ra;
+  if (sync && world > 1) {  // r_col of the other ranks' slots: wait for their row factors in the kernel
+    ra.wait_flags = sync->local_flags;
+    ra.wait_seq = sync->seq;
+    ra.wait_kind = maai::FLAG_R;
+    ra.wait_slot_rows = m_loc;
+    ra.wait_my_slot = rank;
+  }
   return dispatch_tile<true>(d_pad, q_base, rows, z_glob, m_glob, rank * m_loc + row_begin, inv_tau,
-                             r_row + row_begin, r_col, nullptr, acc, b - row_begin, b, s);
+                             r_row + row_begin, r_col, nullptr, acc, b - row_begin, b, s, ra);
 }
 
 static int bwd_dh_impl(const float* dz_acc, const float* dz_extra, const float* rowsum_l, const float* pos_cos,
@@ -715,8 +781,10 @@ static int bwd_check(int b, int world, int rank, int d, int d_pad, int need_mask
 int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, int key_grad,
                     const float* rowsum_l, const float* pos_cos, const void* h1, const void* h2, int in_dtype,
                     const float* inv_norm, const float* grad_loss, int b, int world, int rank, int d, int d_pad,
-                    float inv_tau, int need_mask, void* dh1, void* dh2, float* dz_acc, int flags, void* stream) {
+                    float inv_tau, int need_mask, void* dh1, void* dh2, float* dz_acc, int flags,
+                    const maai_peer_sync* sync, void* stream) {
   if (flags & ~MAAI_F_PREZEROED) return fail(MAAI_E_ARG, "unknown flag");
+  if (check_sync(sync, world) != MAAI_OK) return MAAI_E_ARG;
   if (!z_glob || !r_row || !r_col || !rowsum_l || !pos_cos || !h1 || !h2 || !inv_norm || !grad_loss || !dz_acc)
     return fail(MAAI_E_ARG, "null pointer");
   int rc = bwd_check(b, world, rank, d, d_pad, need_mask);
@@ -727,7 +795,7 @@ int maai_ntxent_bwd(const void* z_glob, const float* r_row, const float* r_col, 
     return fail(MAAI_E_ARG, "z_glob, r_col and dz_acc must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if ((rc = bwd_tiles_impl(z_glob, r_row, r_col, b, world, rank, d_pad, inv_tau, need_mask, dz_acc, s,
-                           flags & MAAI_F_PREZEROED)) != MAAI_OK)
+                           flags & MAAI_F_PREZEROED, sync)) != MAAI_OK)
     return rc;
   return bwd_dh_impl(dz_acc, nullptr, rowsum_l, pos_cos, h1, h2, in_dtype, inv_norm, grad_loss, b, d, d_pad,
                      inv_tau, key_grad, need_mask, dh1, dh2, s);

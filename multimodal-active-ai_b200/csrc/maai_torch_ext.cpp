@@ -33,8 +33,8 @@ void check_rc(int rc, const char* what) {
   TORCH_CHECK(false, msg);
 }
 
-struct Layout {  // one fp32 allocation: [step workspace | r_col] (zero-filled by K1) | inv_norm | pos_cos | loss
-  int64_t ws_words, head, r_len, off_r, off_inv, off_cos, off_loss, total;
+struct Layout {  // one fp32 allocation: [step workspace | r_col] (zero-filled by K1) | inv_norm | pos_cos
+  int64_t ws_words, head, r_len, off_r, off_inv, off_cos, total;
 };
 Layout make_layout(int b, int dp, bool need_bwd) {
   Layout l;
@@ -44,15 +44,15 @@ Layout make_layout(int b, int dp, bool need_bwd) {
   l.off_r = l.ws_words;
   l.off_inv = (l.off_r + l.r_len + 3) / 4 * 4;
   l.off_cos = l.off_inv + 2 * b;
-  l.off_loss = l.off_cos + b;
-  l.total = l.off_loss + 4;
+  l.total = l.off_cos + b;
   return l;
 }
 
 class NTXentFn : public torch::autograd::Function<NTXentFn> {
  public:
+  // need_bwd is decided by the caller (ntxent_loss below): grad mode is switched off inside forward()
   static torch::Tensor forward(torch::autograd::AutogradContext* ctx, torch::Tensor hidden1, torch::Tensor hidden2,
-                               double temperature) {
+                               double temperature, bool need_bwd) {
     const auto h1 = hidden1.contiguous();
     const auto h2 = hidden2.contiguous();
     const int b = (int)h1.size(0), d = (int)h1.size(1);
@@ -60,18 +60,19 @@ class NTXentFn : public torch::autograd::Function<NTXentFn> {
     TORCH_CHECK_VALUE(dp > 0, "embedding dim ", d, " unsupported: the sm_100a tile kernels take 1 <= d <= 256");
     const int dt = dtype_code(h1);
     const float inv_tau = (float)(1.0 / temperature);
-    const bool need_bwd = torch::GradMode::is_enabled() && (hidden1.requires_grad() || hidden2.requires_grad());
     c10::cuda::CUDAGuard guard(h1.device());
     void* st = at::cuda::getCurrentCUDAStream(h1.device().index()).stream();
     const Layout l = make_layout(b, dp, need_bwd);
     auto z = torch::empty({(int64_t)2 * b, (int64_t)dp}, h1.options().dtype(torch::kBFloat16));
     auto buf = torch::empty({l.total}, h1.options().dtype(torch::kFloat32));
+    // the loss is its own tensor: an output that is a view of a buffer created in here gets no grad_fn
+    auto loss = torch::empty({}, h1.options().dtype(torch::kFloat32));
     float* base = buf.data_ptr<float>();
     check_rc(maai_ntxent_normalize(h1.data_ptr(), h2.data_ptr(), b, d, dt, z.data_ptr(), base + l.off_inv,
                                    base + l.off_cos, base, (size_t)(l.ws_words + l.r_len) * 4, st),
              "maai_ntxent_normalize");
     check_rc(maai_ntxent_fwd(z.data_ptr(), b, 1, 0, dp, inv_tau, base + l.off_cos, base,
-                             need_bwd ? base + l.off_r : nullptr, base + l.off_loss, MAAI_F_PREZEROED, st),
+                             need_bwd ? base + l.off_r : nullptr, loss.data_ptr<float>(), MAAI_F_PREZEROED, nullptr, st),
              "maai_ntxent_fwd");
     if (need_bwd) {
       ctx->save_for_backward({h1, h2});
@@ -82,7 +83,7 @@ class NTXentFn : public torch::autograd::Function<NTXentFn> {
       ctx->saved_data["inv_tau"] = (double)inv_tau;
       ctx->saved_data["clean"] = true;
     }
-    return buf.narrow(0, l.off_loss, 1).view({});
+    return loss;
   }
 
   static torch::autograd::variable_list backward(torch::autograd::AutogradContext* ctx,
@@ -109,14 +110,15 @@ class NTXentFn : public torch::autograd::Function<NTXentFn> {
     check_rc(maai_ntxent_bwd(z.data_ptr(), base + l.off_r, base + l.off_r, 1, base, base + l.off_cos, h1.data_ptr(),
                              h2.data_ptr(), dtype_code(h1), base + l.off_inv, g.data_ptr<float>(), b, 1, 0, d, dp,
                              inv_tau, need, (need & 1) ? dh1.data_ptr() : nullptr, (need & 2) ? dh2.data_ptr() : nullptr,
-                             base + l.head, clean ? MAAI_F_PREZEROED : 0, st),
+                             base + l.head, clean ? MAAI_F_PREZEROED : 0, nullptr, st),
              "maai_ntxent_bwd");
-    return {dh1, dh2, torch::Tensor()};
+    return {dh1, dh2, torch::Tensor(), torch::Tensor()};
   }
 };
 
 torch::Tensor ntxent_loss(torch::Tensor hidden1, torch::Tensor hidden2, double temperature) {
-  return NTXentFn::apply(hidden1, hidden2, temperature);
+  const bool need_bwd = torch::GradMode::is_enabled() && (hidden1.requires_grad() || hidden2.requires_grad());
+  return NTXentFn::apply(hidden1, hidden2, temperature, need_bwd);
 }
 
 }  // namespace

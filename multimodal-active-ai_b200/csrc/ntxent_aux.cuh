@@ -28,6 +28,41 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// ---- in-kernel peer synchronisation (include/maai_ntxent.h: maai_peer_sync) ----
+// Flag block of a rank: kFlagKinds x kFlagStride words; word [kind][p] = last step whose stores of that
+// kind rank p has completed into this rank's buffers.
+constexpr int kFlagStride = 32;  // words per kind (world <= 16 today; one 128-byte line per kind)
+enum : int { FLAG_Z = 0, FLAG_R = 1, FLAG_L = 2, kFlagKinds = 3 };
+struct PeerSync {
+  const unsigned long long* peer_flags;  // device array of `world` peer-mapped flag-block addresses; null = off
+  const unsigned int* local_flags;       // this rank's own flag block
+  unsigned int* counter;                 // CTA-done counter of the signalling kernel (zero between uses)
+  unsigned int seq;
+  int world;
+  int rank;
+};
+// Called by threads 0 .. world-1 of ONE CTA after every store of this kernel has been fenced at system
+// scope and ordered before this point (per-thread __threadfence_system + CTA barrier + ticket counter).
+__device__ __forceinline__ void signal_peers(const PeerSync& s, int kind) {
+  if (int(threadIdx.x) < s.world)
+    st_release_sys_u32(reinterpret_cast<unsigned int*>(s.peer_flags[threadIdx.x]) + kind * kFlagStride + s.rank, s.seq);
+}
+// Tail of a multi-CTA producer kernel: every thread has issued its peer stores; the last CTA to get here
+// signals.  Must be reached by all threads of all CTAs (no early return before it).
+__device__ __forceinline__ void signal_when_grid_done(const PeerSync& s, int kind) {
+  if (!s.peer_flags) return;
+  __shared__ unsigned int is_last;
+  __threadfence_system();  // this thread's peer / multicast stores are performed before its CTA's ticket
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(s.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (is_last) {
+    __threadfence_system();  // cumulativity: the other CTAs' fenced stores, observed through the counter
+    signal_peers(s, kind);
+    if (threadIdx.x == 0) *s.counter = 0u;  // ready for the next launch
+  }
+}
+
 constexpr float kNormEps = 1e-12f;  // F.normalize default eps (Objective.py:42-43)
 constexpr int kMaxPerLane = 8;      // d <= 256 -> at most 8 elements per lane
 
@@ -83,35 +118,14 @@ __device__ __forceinline__ void multimem_st_f32(float* a, float v) {
   asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(a), "f"(v) : "memory");
 }
 
-// K1: F.normalize of both views (Objective.py:41-43) -> bf16 rows, 1/norm, positive cosine; one warp per
-// pair k (rows k and b + k of the rank's stacked block); a lane owns DP/32 = VEC consecutive elements of
-// both rows, so the input loads and the bf16 stores are 4..32-byte vectors and a warp moves whole rows.
-// Destinations of the bf16 rows (any combination):
-//   z_local    this rank's (2b, DP) block (single rank, or the NCCL all-gather's send slot)
-//   mc_base    NVSwitch multicast mapping of every rank's (world, 2b, DP) key buffer: ONE multimem.st per
-//              chunk, replicated by the switch                         } the cross-replica gather of
-//   peer_base  table of `world` peer-mapped key buffers: unicast stores } Objective.py:52-53, 102-114 fused
-// Columns [d, DP) are zero so the padded tile MMA sees exact zeros.
-// The kernel also zero-fills `zero_words` 32-bit words at zero_fill (the step's accumulators: row sums,
-// CTA-done counter, dz accumulator), which removes the separate memset / zero kernels of the step.
+// body of K1 for one pair (see normalize_cast_kernel below)
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256)
-normalize_cast_kernel(const T* __restrict__ h1, const T* __restrict__ h2, int b, int d, bool vec_ok,
-                      __nv_bfloat16* __restrict__ z_local, const unsigned long long* __restrict__ peer_base,
-                      unsigned long long mc_base, int world, int rank, float* __restrict__ inv_norm,
-                      float* __restrict__ pos_cos, uint32_t* __restrict__ zero_fill, size_t zero_words) {
+__device__ __forceinline__ void normalize_pair(const T* __restrict__ h1, const T* __restrict__ h2, int b, int d, bool vec_ok,
+                                               __nv_bfloat16* __restrict__ z_local,
+                                               const unsigned long long* __restrict__ peer_base, unsigned long long mc_base,
+                                               int world, int rank, float* __restrict__ inv_norm,
+                                               float* __restrict__ pos_cos, int k, int lane) {
   constexpr int DP = VEC * 32;
-  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  pdl_launch_dependents<1>();
-  pdl_wait();
-  if (zero_words) {  // grid-strided 16-byte stores (zero_fill is 16-byte aligned, checked by the host)
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
-    uint4* p4 = reinterpret_cast<uint4*>(zero_fill);
-    for (size_t i = tid; i < zero_words / 4; i += nth) p4[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (size_t i = (zero_words / 4) * 4 + tid; i < zero_words; i += nth) zero_fill[i] = 0u;
-  }
-  if (k >= b) return;
   float a[VEC], c[VEC];
   load_row_chunk<T, VEC>(h1 + (size_t)k * d, lane * VEC, d, vec_ok, a);
   load_row_chunk<T, VEC>(h2 + (size_t)k * d, lane * VEC, d, vec_ok, c);
@@ -159,6 +173,39 @@ normalize_cast_kernel(const T* __restrict__ h1, const T* __restrict__ h2, int b,
   }
 }
 
+// K1: F.normalize of both views (Objective.py:41-43) -> bf16 rows, 1/norm, positive cosine; one warp per
+// pair k (rows k and b + k of the rank's stacked block); a lane owns DP/32 = VEC consecutive elements of
+// both rows, so the input loads and the bf16 stores are 4..32-byte vectors and a warp moves whole rows.
+// Destinations of the bf16 rows (any combination):
+//   z_local    this rank's (2b, DP) block (single rank, or the NCCL all-gather's send slot)
+//   mc_base    NVSwitch multicast mapping of every rank's (world, 2b, DP) key buffer: ONE multimem.st per
+//              chunk, replicated by the switch                         } the cross-replica gather of
+//   peer_base  table of `world` peer-mapped key buffers: unicast stores } Objective.py:52-53, 102-114 fused
+// Columns [d, DP) are zero so the padded tile MMA sees exact zeros.
+// The kernel also zero-fills `zero_words` 32-bit words at zero_fill (the step's accumulators: row sums,
+// CTA-done counter, dz accumulator), which removes the separate memset / zero kernels of the step.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+normalize_cast_kernel(const T* __restrict__ h1, const T* __restrict__ h2, int b, int d, bool vec_ok,
+                      __nv_bfloat16* __restrict__ z_local, const unsigned long long* __restrict__ peer_base,
+                      unsigned long long mc_base, int world, int rank, float* __restrict__ inv_norm,
+                      float* __restrict__ pos_cos, uint32_t* __restrict__ zero_fill, size_t zero_words,
+                      const __grid_constant__ PeerSync sync) {
+  constexpr int DP = VEC * 32;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  pdl_launch_dependents<1>();
+  pdl_wait();
+  if (zero_words) {  // grid-strided 16-byte stores (zero_fill is 16-byte aligned, checked by the host)
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    uint4* p4 = reinterpret_cast<uint4*>(zero_fill);
+    for (size_t i = tid; i < zero_words / 4; i += nth) p4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (size_t i = (zero_words / 4) * 4 + tid; i < zero_words; i += nth) zero_fill[i] = 0u;
+  }
+  if (k < b) normalize_pair<T, VEC>(h1, h2, b, d, vec_ok, z_local, peer_base, mc_base, world, rank, inv_norm, pos_cos, k, lane);
+  signal_when_grid_done(sync, FLAG_Z);  // in-kernel replacement of the barrier launch behind the gather
+}
+
 // K1 for chained views.  The reference's training loop feeds this step's
 // outputs2 to the next step as hidden1 (Contrastive_Learning.py:700 "outputs1 = outputs2", consumed
 // detached at :685), so the view-a rows of EVERY rank at step t are the view-b rows of step t-1, which
@@ -173,7 +220,8 @@ normalize_chain_kernel(const T* __restrict__ h2, int b, int d, bool vec_ok,
                        const __nv_bfloat16* __restrict__ z_prev, const float* __restrict__ inv_prev,
                        __nv_bfloat16* __restrict__ z_new, const unsigned long long* __restrict__ peer_base,
                        unsigned long long mc_base, int world, int rank, float* __restrict__ inv_norm,
-                       float* __restrict__ pos_cos, uint32_t* __restrict__ zero_fill, size_t zero_words) {
+                       float* __restrict__ pos_cos, uint32_t* __restrict__ zero_fill, size_t zero_words,
+                       const __grid_constant__ PeerSync sync) {
   constexpr int DP = VEC * 32;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -185,7 +233,7 @@ normalize_chain_kernel(const T* __restrict__ h2, int b, int d, bool vec_ok,
     for (size_t i = tid; i < zero_words / 4; i += nth) p4[i] = make_uint4(0u, 0u, 0u, 0u);
     for (size_t i = (zero_words / 4) * 4 + tid; i < zero_words; i += nth) zero_fill[i] = 0u;
   }
-  if (k >= b) return;
+  if (k < b) {
   using Vec = typename std::conditional<VEC == 2, uint32_t, typename std::conditional<VEC == 4, uint2, uint4>::type>::type;
   float c[VEC];
   load_row_chunk<T, VEC>(h2 + (size_t)k * d, lane * VEC, d, vec_ok, c);
@@ -224,6 +272,8 @@ normalize_chain_kernel(const T* __restrict__ h2, int b, int d, bool vec_ok,
     inv_norm[b + k] = ic;
     pos_cos[k] = dot;
   }
+  }
+  signal_when_grid_done(sync, FLAG_Z);
 }
 
 // Per-row tail of the forward (Objective.py:76-79): with e_pos = exp((cos_pos - 1)/tau) and l' = sum over
@@ -247,6 +297,8 @@ struct FinalizeArgs {
   int my_rank;
   float* mc_r;
   const unsigned long long* stage_tab;
+  PeerSync sync;  // peer_flags != null: signal FLAG_R once the row factors have been stored to every rank
+                  // (and, with stage_tab, wait for every peer's FLAG_L before pulling its staged sums)
 };
 __device__ __forceinline__ double finalize_rows(const FinalizeArgs& f, int tid, int nth) {
   double acc = 0.0;
@@ -306,15 +358,29 @@ finalize_loss_kernel(const __grid_constant__ FinalizeArgs f) {
   const unsigned rank = cluster.block_rank();
   pdl_launch_dependents<8>();
   pdl_wait();
+  if (f.stage_tab && f.sync.peer_flags) {
+    // cross-rank symmetric forward: the peers' staged partial sums (maai_ntxent_fwd_sym_tiles on THEIR GPUs)
+    // must be complete before they are pulled: one waiting thread per peer, then the CTA barrier
+    if (int(threadIdx.x) < f.world && int(threadIdx.x) != f.my_rank)
+      wait_flag_ge(f.sync.local_flags + FLAG_L * kFlagStride + threadIdx.x, f.sync.seq);
+    __syncthreads();
+  }
   const double acc = finalize_rows(f, rank * blockDim.x + threadIdx.x, kFinalizeCluster * blockDim.x);
+  if (f.sync.peer_flags) __threadfence_system();  // this thread's row-factor stores, before the cluster barrier
   const double v = finalize_block_sum(acc, part);
   if (threadIdx.x == 0) cluster.map_shared_rank(cta_part, 0)[rank] = v;
   cluster.sync();
-  if (rank == 0 && threadIdx.x == 0) {
-    double t = 0.0;
+  if (rank == 0) {
+    if (threadIdx.x == 0) {
+      double t = 0.0;
 #pragma unroll
-    for (int r = 0; r < kFinalizeCluster; ++r) t += cta_part[r];
-    *f.loss_out = float(t / double(f.b));
+      for (int r = 0; r < kFinalizeCluster; ++r) t += cta_part[r];
+      *f.loss_out = float(t / double(f.b));
+    }
+    if (f.sync.peer_flags) {  // all 8 CTAs have fenced their stores and passed the cluster barrier
+      __threadfence_system();
+      signal_peers(f.sync, FLAG_R);
+    }
   }
 }
 

@@ -171,6 +171,18 @@ struct TileParams {
   // done_ctr: zero-initialised 32-bit counter (K1's zero fill); null = no in-kernel finalize.
   unsigned int* done_ctr;
   FinalizeArgs fin;
+  // Multi-rank, optional (null = the caller ordered the gathers with a barrier launch): before the TMA
+  // producer first touches rows of rank slot s != wait_my_slot it waits until word [wait_kind][s] of this
+  // rank's flag block has reached wait_seq -- FWD: the peer's bf16 rows (FLAG_Z) for key tiles and, in the
+  // cross-rank symmetric forward, remote anchor tiles; BWD: the peer's row factors (FLAG_R) for r_col.
+  const unsigned int* wait_flags;
+  unsigned int wait_seq;
+  int wait_kind;
+  int wait_what;       // 1: key tiles / r_col (rows of the gathered buffer), 2: anchor tiles of the GRP groups
+  int wait_slot_rows;  // rows per rank slot (2b)
+  int wait_my_slot;
+  // GRP: the last CTA signals FLAG_L (this rank's staged partial sums are complete) through grp_sync
+  PeerSync grp_sync;
 };
 
 template <int D, bool BWD, int NQ>
@@ -397,6 +409,20 @@ struct GrpWalk {
   }
 };
 
+// TMA producer, multi-rank: wait until the rank slots that own global rows [row0, last] have signalled
+// (TileParams::wait_*); returns the updated "seen" mask.  Out of line: called a handful of times per CTA.
+__device__ __noinline__ uint32_t ensure_slots(const TileParams& p, uint32_t seen, int row0, int last) {
+  bool waited = false;
+  for (int sl = row0 / p.wait_slot_rows; sl <= last / p.wait_slot_rows; ++sl)
+    if (!((seen >> sl) & 1u)) {
+      wait_flag_ge(p.wait_flags + p.wait_kind * kFlagStride + sl, p.wait_seq);
+      seen |= 1u << sl;
+      waited = true;
+    }
+  if (waited) fence_proxy_async_all();  // the TMA (async proxy) reads what the peers' stores wrote
+  return seen;
+}
+
 // Forward, last CTA done: every other CTA's sums are in L2 (their threads fenced before the CTA took its
 // ticket), so this CTA runs the per-row tail (finalize_rows) over all 2b rows.  Out of line on purpose: it
 // runs once per launch and must not cost the hot loops a register.  flag_smem / part_smem: shared-window
@@ -408,8 +434,15 @@ __device__ __noinline__ void fwd_tail_finalize(const TileParams& p, uint32_t fla
   if (*flag) {
     __threadfence();
     double* part = static_cast<double*>(__cvta_shared_to_generic(part_smem));
-    const double v = finalize_block_sum(finalize_rows(p.fin, threadIdx.x, blockDim.x), part);
+    const double acc = finalize_rows(p.fin, threadIdx.x, blockDim.x);
+    if (p.fin.sync.peer_flags) __threadfence_system();  // this thread's row-factor stores to the peers
+    const double v = finalize_block_sum(acc, part);     // (contains a CTA barrier)
     if (threadIdx.x == 0) *p.fin.loss_out = float(v / double(p.fin.b));
+    if (p.fin.sync.peer_flags) {
+      __syncthreads();
+      __threadfence_system();
+      signal_peers(p.fin.sync, FLAG_R);
+    }
   }
 }
 
@@ -501,11 +534,18 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       PROF_INIT();
       uint32_t t = 0, useg = 0;
       Walk walk(p);
+      // rank slots whose rows are known to have landed (in-kernel replacement of the gather barrier)
+      uint32_t seen = p.wait_flags ? (1u << p.wait_my_slot) : 0xffffffffu;
+      auto ensure_rows = [&](int row0, int nrows, int limit) {
+        if (seen != 0xffffffffu) seen = ensure_slots(p, seen, row0, min(row0 + nrows, limit) - 1);
+      };
       for (long long it = it_begin; it < it_end;) {
         int rb, j0, n;
         walk.locate(it, it_end, rb, j0, n);
         mbar_wait(bar_q_empty, (useg & 1) ^ 1);
         PROF_MARK(0);
+        if (GRP && p.wait_what == 2)
+          ensure_rows(p.g_qrow0[walk.g] + rb * C::RB_ROWS, C::RB_ROWS, p.g_qrow0[walk.g] + p.g_rows[walk.g]);
         mbar_arrive_expect_tx(bar_q_full, NQ * C::TILE_BYTES);
 #pragma unroll
         for (int q = 0; q < NQ; ++q)
@@ -521,6 +561,7 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
             mbar_arrive(bar_k_full(st));
             continue;
           }
+          if (p.wait_what == 1) ensure_rows((j0 + jj) * C::KT, C::KT, p.m_glob);
           mbar_arrive_expect_tx(bar_k_full(st), C::TILE_BYTES + (BWD ? C::KT * 4 : 0));
 #pragma unroll
           for (int c = 0; c < C::CHUNKS; ++c)
@@ -1071,6 +1112,8 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
   if (!BWD && !GRP && p.done_ctr) fwd_tail_finalize(p, smem_base + C::OFF_BAR, smem_base + C::OFF_Q);
+  // cross-rank symmetric forward: the staged partial sums for the peers are complete once every CTA is here
+  if (GRP) signal_when_grid_done(p.grp_sync, FLAG_L);
 }
 
 }  // namespace maai

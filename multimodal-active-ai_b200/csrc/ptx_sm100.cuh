@@ -40,6 +40,39 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
+// Cross-GPU flags (system scope): the in-kernel replacement of the symmetric-memory barrier launches
+// ----------------------------------------------------------------------------------------------
+// A producer rank signals "my stores of step `seq` have landed in your buffers" by a release store of
+// `seq` into ITS word of every peer's flag block (peer-mapped NVLink address); a consumer spins on its
+// LOCAL flag block with acquire loads until the word has reached `seq` (sequence numbers only grow, so
+// there is nothing to reset).  Bounded like mbar_wait: a protocol bug traps, it never hangs the GPU.
+__device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// generic-proxy observations (the acquire above) before async-proxy reads (TMA loads of what the peer wrote)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// slow path out of line: the callers' hot loops must not pay registers / stack for the spin and its printf
+__device__ __noinline__ void wait_flag_spin(const unsigned int* flag, unsigned int seq) {
+  const long long t0 = clock64();
+  while (int(ld_acquire_sys_u32(flag) - seq) < 0) {
+    if (clock64() - t0 > 6000000000LL) {  // ~3 s: a peer that never signals (crashed rank, protocol bug)
+      printf("maai: peer flag wait timeout block %d thread %d flag %p want %u have %u\n", blockIdx.x, threadIdx.x,
+             (const void*)flag, seq, ld_acquire_sys_u32(flag));
+      __trap();
+    }
+    __nanosleep(64);
+  }
+}
+__device__ __forceinline__ void wait_flag_ge(const unsigned int* flag, unsigned int seq) {
+  if (int(ld_acquire_sys_u32(flag) - seq) < 0) wait_flag_spin(flag, seq);
+}
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

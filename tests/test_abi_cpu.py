@@ -44,31 +44,38 @@ def test_c_abi_argument_errors_without_gpu():
     # null pointers / bad sizes are rejected before any CUDA call
     assert lib.maai_ntxent_normalize(None, None, 4, 8, 0, None, None, None, None, 0, None) == _lib.E_ARG
     assert b"null" in lib.maai_last_error()
-    assert lib.maai_ntxent_fwd(None, 4, 1, 0, 64, 1.0, None, None, None, None, 0, None) == _lib.E_ARG
+    assert lib.maai_ntxent_fwd(None, 4, 1, 0, 64, 1.0, None, None, None, None, 0, None, None) == _lib.E_ARG
     # the later entry points validate the same way (ABI v4 / v5)
     assert lib.maai_ntxent_bwd_tiles(None, None, None, 4, 1, 0, 64, 1.0, 3, None, None) == _lib.E_ARG
     assert lib.maai_ntxent_bwd_keyside(None, None, 4, 2, 0, 64, 1.0, None, None) == _lib.E_ARG
     assert lib.maai_ntxent_bwd_dh(None, None, None, None, None, None, 0, None, None, 4, 8, 64, 1.0, 1, 3,
                                   None, None, None) == _lib.E_ARG
-    assert lib.maai_ntxent_fwd_sym_tiles(None, 4, 2, 0, 64, 1.0, None, None, 0, None) == _lib.E_ARG
-    assert lib.maai_ntxent_fwd_sym_finalize(None, None, 4, 2, 0, 1.0, None, None, None, None, None, None) == _lib.E_ARG
+    assert lib.maai_ntxent_fwd_sym_tiles(None, 4, 2, 0, 64, 1.0, None, None, 0, None, None) == _lib.E_ARG
+    assert lib.maai_ntxent_fwd_sym_finalize(None, None, 4, 2, 0, 1.0, None, None, None, None, None, None, None) == _lib.E_ARG
     import ctypes
     buf = (ctypes.c_float * 64)()
     ptr = ctypes.cast(buf, ctypes.c_void_p)
     # bad rank / world / width with non-null pointers: still no CUDA call
-    assert lib.maai_ntxent_fwd_sym_tiles(ptr, 4, 2, 2, 64, 1.0, ptr, ptr, 0, None) == _lib.E_ARG
-    assert lib.maai_ntxent_fwd_sym_tiles(ptr, 4, 17, 0, 64, 1.0, ptr, ptr, 0, None) == _lib.E_SHAPE
+    assert lib.maai_ntxent_fwd_sym_tiles(ptr, 4, 2, 2, 64, 1.0, ptr, ptr, 0, None, None) == _lib.E_ARG
+    assert lib.maai_ntxent_fwd_sym_tiles(ptr, 4, 17, 0, 64, 1.0, ptr, ptr, 0, None, None) == _lib.E_SHAPE
     assert lib.maai_ntxent_bwd_keyside(ptr, ptr, 4, 2, 0, 96, 1.0, ptr, None) == _lib.E_SHAPE
     # ABI v6: step workspace, flags, zero-fill arguments
     assert lib.maai_ntxent_workspace_bytes(100, 128, 0) == 256 * 4
     assert lib.maai_ntxent_workspace_bytes(100, 128, 1) == (256 + 200 * 128) * 4
     assert lib.maai_ntxent_workspace_bytes(100, 96, 1) == 0 and lib.maai_ntxent_workspace_bytes(0, 128, 1) == 0
-    assert lib.maai_ntxent_fwd(ptr, 4, 1, 0, 64, 1.0, ptr, ptr, None, ptr, 2, None) == _lib.E_ARG  # unknown flag
+    assert lib.maai_ntxent_fwd(ptr, 4, 1, 0, 64, 1.0, ptr, ptr, None, ptr, 2, None, None) == _lib.E_ARG  # unknown flag
     assert b"flag" in lib.maai_last_error()
     assert lib.maai_ntxent_normalize(ptr, ptr, 4, 8, 0, ptr, ptr, ptr, ptr, 6, None) == _lib.E_ARG  # zero_bytes % 4
     assert lib.maai_ntxent_normalize(ptr, ptr, 4, 8, 0, ptr, ptr, ptr, None, 16, None) == _lib.E_ARG
     assert lib.maai_ntxent_fwd_is_symmetric(4096, 1, 128) == 1 and lib.maai_ntxent_fwd_is_symmetric(4096, 2, 128) == 0
     assert lib.maai_ntxent_fwd_is_symmetric(2048, 1, 256) == 0 and lib.maai_ntxent_fwd_is_symmetric(8192, 1, 256) == 1
+    # ABI v7: maai_peer_sync is validated on the host (null members, seq 0) before any CUDA call
+    bad = _lib.PeerSync(None, None, None, 1)
+    assert lib.maai_ntxent_fwd(ptr, 4, 2, 0, 64, 1.0, ptr, ptr, None, ptr, 0, ctypes.byref(bad), None) == _lib.E_ARG
+    assert b"maai_peer_sync" in lib.maai_last_error()
+    bad = _lib.PeerSync(ptr.value, ptr.value, ptr.value, 0)
+    assert lib.maai_ntxent_bwd(ptr, ptr, ptr, 1, ptr, ptr, ptr, ptr, 0, ptr, ptr, 4, 2, 0, 8, 64, 1.0, 3, ptr, ptr, ptr, 0,
+                               ctypes.byref(bad), None) == _lib.E_ARG
     with pytest.raises(ValueError):
         _lib.check(_lib.E_SHAPE, "x")
     with pytest.raises(_lib.MaaiError):

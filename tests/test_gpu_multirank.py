@@ -47,7 +47,7 @@ def test_emulated_ranks_one_gpu(world, b, d, tau):
     for p in range(world):
         _lib.check(lib.maai_ntxent_fwd(z_all.data_ptr(), b, world, p, dp, 1.0 / tau, cos[p].data_ptr(),
                                        rowsum[p].data_ptr(), r_col[p * 2 * b:].data_ptr(),
-                                       losses[p:].data_ptr(), 0, s), "k2")
+                                       losses[p:].data_ptr(), 0, None, s), "k2")
     ol, o1q, o2q = O.contrastive_loss_oracle_distributed([h.numpy() for h in h1r], [h.numpy() for h in h2r], tau, key_grad=False)
     _, o1f, o2f = O.contrastive_loss_oracle_distributed([h.numpy() for h in h1r], [h.numpy() for h in h2r], tau, key_grad=True)
     got = losses.cpu().numpy()
@@ -64,7 +64,7 @@ def test_emulated_ranks_one_gpu(world, b, d, tau):
                                            (r_col if key_grad else zeros).data_ptr(), key_grad,
                                            rowsum[p].data_ptr(), cos[p].data_ptr(), dh[p][0].data_ptr(),
                                            dh[p][1].data_ptr(), 0, inv[p].data_ptr(), one.data_ptr(), b, world, p,
-                                           d, dp, 1.0 / tau, 3, g1.data_ptr(), g2.data_ptr(), acc.data_ptr(), 0, s), "k3")
+                                           d, dp, 1.0 / tau, 3, g1.data_ptr(), g2.data_ptr(), acc.data_ptr(), 0, None, s), "k3")
             torch.cuda.synchronize()
             assert rel_fro(g1.cpu().numpy(), r1[p]) <= 1e-2, (p, key_grad)
             assert rel_fro(g2.cpu().numpy(), r2[p]) <= 1e-2, (p, key_grad)
@@ -134,7 +134,7 @@ def test_emulated_ranks_reduce_scatter_dataflow(world, b, d, tau):
     losses = torch.zeros(world, device=dev)
     for p in range(world):
         _lib.check(lib.maai_ntxent_fwd(z_all.data_ptr(), b, world, p, dp, 1.0 / tau, cos[p].data_ptr(),
-                                       rowsum[p].data_ptr(), r_loc[p].data_ptr(), losses[p:].data_ptr(), 0, s), "k2")
+                                       rowsum[p].data_ptr(), r_loc[p].data_ptr(), losses[p:].data_ptr(), 0, None, s), "k2")
     # every rank's key-side partial sums for ALL anchors, then the reduce-scatter (sum over ranks)
     total = torch.zeros(world * 2 * b, dp, device=dev)
     for p in range(world):
@@ -193,13 +193,13 @@ def test_emulated_ranks_symmetric_forward(world, b, d, tau):
     loss_full = torch.zeros(world, device=dev)
     for p in range(world):
         _lib.check(lib.maai_ntxent_fwd(z_all.data_ptr(), b, world, p, dp, 1.0 / tau, cos[p].data_ptr(),
-                                       rowsum_full[p].data_ptr(), r_full[p].data_ptr(), loss_full[p:].data_ptr(), 0, s), "k2")
+                                       rowsum_full[p].data_ptr(), r_full[p].data_ptr(), loss_full[p:].data_ptr(), 0, None, s), "k2")
     # symmetric: tile part of every rank, "barrier", then the finalize of every rank
     rowsum = torch.full((world, 2 * b), float("nan"), device=dev)
     stage = torch.full((world, world, 2 * b), float("nan"), device=dev)  # stage[p] = rank p's staging vectors
     for p in range(world):
         _lib.check(lib.maai_ntxent_fwd_sym_tiles(z_all.data_ptr(), b, world, p, dp, 1.0 / tau, rowsum[p].data_ptr(),
-                                                 stage[p].data_ptr(), 0, s), "sym tiles")
+                                                 stage[p].data_ptr(), 0, None, s), "sym tiles")
     torch.cuda.synchronize()
     tab = torch.tensor([stage[p].data_ptr() for p in range(world)], dtype=torch.int64, device=dev)
     r_sym = torch.zeros(world, 2 * b, device=dev)
@@ -207,7 +207,7 @@ def test_emulated_ranks_symmetric_forward(world, b, d, tau):
     for p in range(world):
         _lib.check(lib.maai_ntxent_fwd_sym_finalize(rowsum[p].data_ptr(), tab.data_ptr(), b, world, p, 1.0 / tau,
                                                     cos[p].data_ptr(), r_sym[p].data_ptr(), None, None,
-                                                    loss_sym[p:].data_ptr(), s), "sym finalize")
+                                                    loss_sym[p:].data_ptr(), None, s), "sym finalize")
     torch.cuda.synchronize()
     # (polynomial / MUFU exp2 assignment differs between the two tile walks: agreement to ~1e-4, not bitwise)
     assert torch.allclose(rowsum, rowsum_full, rtol=2e-3, atol=1e-6), (rowsum - rowsum_full).abs().max()
@@ -228,3 +228,86 @@ def test_two_gpu_torchrun(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "DIST_OK" in res.stdout
+
+
+@pytest.mark.parametrize("world,b,d,tau,sym", [(2, 96, 128, 0.5, False), (4, 200, 64, 0.1, False), (8, 64, 128, 0.5, False),
+                                               (3, 130, 256, 0.2, False), (2, 700, 128, 0.2, True), (4, 200, 64, 0.1, True),
+                                               (5, 300, 128, 0.3, True)])
+def test_emulated_ranks_inkernel_flags(world, b, d, tau, sym):
+    """The in-kernel peer synchronisation (maai_peer_sync): every emulated rank has its own key buffer, row-factor
+    array, staging vectors and FLAG BLOCK on the one GPU; K1 stores into all buffers and signals, the forward's
+    TMA producer waits per rank slot, the finalize stores the row factors everywhere and signals, the
+    backward waits per slot before reading r_col.  Two consecutive steps (sequence numbers 1, 2) with
+    different inputs; losses and full gradients against the fp64 oracle.  (Ranks run one after the other
+    here, so every flag is already set when it is waited for; real concurrency is tests/_dist_gpu_worker.py.)"""
+    import ctypes
+    from maai_b200 import _lib
+    from oracle import ntxent_oracle as O
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    s = torch.cuda.current_stream().cuda_stream
+    dp = lib.maai_padded_dim(d)
+    r_len = lib.maai_ntxent_r_len(b, world)
+    zbuf = [torch.zeros(world, 2 * b, dp, dtype=torch.bfloat16, device=dev) for _ in range(world)]
+    rbuf = [torch.zeros(r_len, device=dev) for _ in range(world)]
+    stage = [torch.zeros(world, 2 * b, device=dev) for _ in range(world)]
+    flags = [torch.zeros(_lib.FLAG_WORDS, dtype=torch.int32, device=dev) for _ in range(world)]
+    ctr = [torch.zeros(4, dtype=torch.int32, device=dev) for _ in range(world)]
+    tab = lambda ts: torch.tensor([t.data_ptr() for t in ts], dtype=torch.int64, device=dev)
+    z_tab, r_tab, s_tab, f_tab = tab(zbuf), tab(rbuf), tab(stage), tab(flags)
+    one = torch.ones((), device=dev)
+    for seq in (1, 2):
+        g = torch.Generator().manual_seed(world * 131 + b + seq)
+        H1 = torch.randn(world * b, d, generator=g)
+        H2 = H1 + 0.5 * torch.randn(world * b, d, generator=g)
+        h = [(H1[p * b:(p + 1) * b].contiguous().to(dev), H2[p * b:(p + 1) * b].contiguous().to(dev)) for p in range(world)]
+        sync = [_lib.PeerSync(f_tab.data_ptr(), flags[p].data_ptr(), ctr[p].data_ptr(), seq) for p in range(world)]
+        inv = torch.zeros(world, 2 * b, device=dev); cos = torch.zeros(world, b, device=dev)
+        wsb = lib.maai_ntxent_workspace_bytes(b, dp, 1) // 4
+        head = (2 * b + _lib.WS_CTL_WORDS + 127) // 128 * 128
+        ws = [torch.full((wsb,), float("nan"), device=dev) for _ in range(world)]
+        for p in range(world):
+            _lib.check(lib.maai_ntxent_normalize_peer(h[p][0].data_ptr(), h[p][1].data_ptr(), b, d, 0, z_tab.data_ptr(), None,
+                                                      world, p, inv[p].data_ptr(), cos[p].data_ptr(), ws[p].data_ptr(),
+                                                      wsb * 4, ctypes.byref(sync[p]), s), "k1 peer")
+        torch.cuda.synchronize()
+        for p in range(world):
+            f = flags[p].cpu().numpy()
+            assert (f[:world] == seq).all(), f[:world]          # kind 0 (rows) from every rank
+            assert int(ctr[p][0]) == 0                            # the CTA counter reset itself
+        losses = torch.zeros(world, device=dev)
+        for p in range(world):
+            if sym:
+                _lib.check(lib.maai_ntxent_fwd_sym_tiles(zbuf[p].data_ptr(), b, world, p, dp, 1.0 / tau, ws[p].data_ptr(),
+                                                         stage[p].data_ptr(), _lib.F_PREZEROED, ctypes.byref(sync[p]), s), "sym tiles")
+            else:
+                _lib.check(lib.maai_ntxent_fwd_peer(zbuf[p].data_ptr(), b, world, p, dp, 1.0 / tau, cos[p].data_ptr(),
+                                                    ws[p].data_ptr(), r_tab.data_ptr(), None, losses[p:].data_ptr(),
+                                                    _lib.F_PREZEROED, ctypes.byref(sync[p]), s), "fwd peer")
+        if sym:
+            torch.cuda.synchronize()
+            for p in range(world):
+                assert (flags[p].cpu().numpy()[64:64 + world] == seq).all()   # kind 2 (staged sums) from every rank
+            for p in range(world):
+                _lib.check(lib.maai_ntxent_fwd_sym_finalize(ws[p].data_ptr(), s_tab.data_ptr(), b, world, p, 1.0 / tau,
+                                                            cos[p].data_ptr(), None, r_tab.data_ptr(), None,
+                                                            losses[p:].data_ptr(), ctypes.byref(sync[p]), s), "sym finalize")
+        torch.cuda.synchronize()
+        for p in range(world):
+            assert (flags[p].cpu().numpy()[32:32 + world] == seq).all()       # kind 1 (row factors) from every rank
+        hr1 = [H1[p * b:(p + 1) * b].numpy() for p in range(world)]
+        hr2 = [H2[p * b:(p + 1) * b].numpy() for p in range(world)]
+        ol, o1, o2 = O.contrastive_loss_oracle_distributed(hr1, hr2, tau, key_grad=True)
+        got = losses.cpu().numpy()
+        for p in range(world):
+            assert abs(got[p] - ol[p]) <= 1e-3 * abs(ol[p]), (seq, p)
+            assert torch.equal(rbuf[p], rbuf[0])                  # every rank holds the same gathered row factors
+            g1 = torch.zeros(b, d, device=dev); g2 = torch.zeros(b, d, device=dev)
+            r_row = rbuf[p][p * 2 * b:(p + 1) * 2 * b]
+            _lib.check(lib.maai_ntxent_bwd(zbuf[p].data_ptr(), r_row.data_ptr(), rbuf[p].data_ptr(), 1, ws[p].data_ptr(),
+                                           cos[p].data_ptr(), h[p][0].data_ptr(), h[p][1].data_ptr(), 0, inv[p].data_ptr(),
+                                           one.data_ptr(), b, world, p, d, dp, 1.0 / tau, 3, g1.data_ptr(), g2.data_ptr(),
+                                           ws[p][head:].data_ptr(), _lib.F_PREZEROED, ctypes.byref(sync[p]), s), "bwd")
+            torch.cuda.synchronize()
+            assert rel_fro(g1.cpu().numpy(), o1[p]) <= 1e-2, (seq, p)
+            assert rel_fro(g2.cpu().numpy(), o2[p]) <= 1e-2, (seq, p)

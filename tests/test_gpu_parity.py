@@ -279,11 +279,11 @@ def test_c_abi_is_cuda_graph_capturable():
             _lib.check(lib.maai_ntxent_normalize(t.h1.data_ptr(), t.h2.data_ptr(), b, d, 0, t.z.data_ptr(),
                                                  t.inv.data_ptr(), t.cos.data_ptr(), None, 0, stream), "k1")
             _lib.check(lib.maai_ntxent_fwd(t.z.data_ptr(), b, 1, 0, dp, 1.0 / tau, t.cos.data_ptr(), t.l.data_ptr(),
-                                           t.r.data_ptr(), t.loss.data_ptr(), 0, stream), "k2")
+                                           t.r.data_ptr(), t.loss.data_ptr(), 0, None, stream), "k2")
             _lib.check(lib.maai_ntxent_bwd(t.z.data_ptr(), t.r.data_ptr(), t.r.data_ptr(), 1, t.l.data_ptr(),
                                            t.cos.data_ptr(), t.h1.data_ptr(), t.h2.data_ptr(), 0, t.inv.data_ptr(),
                                            one.data_ptr(), b, 1, 0, d, dp, 1.0 / tau, 3, t.g1.data_ptr(),
-                                           t.g2.data_ptr(), t.acc.data_ptr(), 0, stream), "k3")
+                                           t.g2.data_ptr(), t.acc.data_ptr(), 0, None, stream), "k3")
 
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):

@@ -58,7 +58,7 @@ def run_case(b, d, tau, world=1, rank=0, seed=0, aligned=False, verbose=True):
     loss = torch.zeros((), device=dev)
     t0 = time.time()
     _lib.check(lib.maai_ntxent_fwd(z_all.data_ptr(), b, world, rank, dp, 1.0 / tau, cos_all[rank].data_ptr(),
-                                   rowsum.data_ptr(), r_row.data_ptr(), loss.data_ptr(), 0, s), "fwd")
+                                   rowsum.data_ptr(), r_row.data_ptr(), loss.data_ptr(), 0, None, s), "fwd")
     torch.cuda.synchronize()
     out["fwd_ms_first"] = (time.time() - t0) * 1e3
     out["cos_maxabs"] = float(np.abs(cos_all[rank].cpu().numpy() - S[rows[:b], pos[:b]]).max())
@@ -82,7 +82,7 @@ def run_case(b, d, tau, world=1, rank=0, seed=0, aligned=False, verbose=True):
     _lib.check(lib.maai_ntxent_bwd(z_all.data_ptr(), r_row.data_ptr(), r_col.data_ptr(), 1,
                                    rowsum.data_ptr(), cos_all[rank].data_ptr(), h1.data_ptr(), h2.data_ptr(), 0, inv_all[rank].data_ptr(), gl.data_ptr(),
                                    b, world, rank, d, dp, 1.0 / tau, 3, dh1.data_ptr(), dh2.data_ptr(),
-                                   dz_acc.data_ptr(), 0, s), "bwd")
+                                   dz_acc.data_ptr(), 0, None, s), "bwd")
     torch.cuda.synchronize()
     A = dz_acc.cpu().double().numpy()
     out["A_rel_fro"] = float(np.linalg.norm(A - A_ref) / np.linalg.norm(A_ref))

@@ -47,16 +47,16 @@ def main():
         stage = torch.zeros(world, 2 * b, device=dev)
         for p in sorted({0, world // 2, world - 1}):
             t_full = timeit(lambda: _lib.check(lib.maai_ntxent_fwd(z.data_ptr(), b, world, p, dp, 2.0, cos.data_ptr(),
-                                                                   rowsum.data_ptr(), r.data_ptr(), loss.data_ptr(), 0, s), "f"))
+                                                                   rowsum.data_ptr(), r.data_ptr(), loss.data_ptr(), 0, None, s), "f"))
             t_sym = timeit(lambda: _lib.check(lib.maai_ntxent_fwd_sym_tiles(z.data_ptr(), b, world, p, dp, 2.0,
-                                                                            rowsum.data_ptr(), stage.data_ptr(), 0, s), "s"))
+                                                                            rowsum.data_ptr(), stage.data_ptr(), 0, None, s), "s"))
             print(f"world={world} rank={p} b={b} d={d}: full fwd (+finalize) {t_full:.4f} ms, sym tiles {t_sym:.4f} ms", flush=True)
         if world == worlds[0]:
             z1 = z.reshape(1, -1, dp)
             bb = B
             cos1 = torch.zeros(bb, device=dev); rs1 = torch.zeros(2 * bb, device=dev); r1 = torch.zeros(2 * bb, device=dev)
             t1 = timeit(lambda: _lib.check(lib.maai_ntxent_fwd(z1.data_ptr(), bb, 1, 0, dp, 2.0, cos1.data_ptr(),
-                                                               rs1.data_ptr(), r1.data_ptr(), loss.data_ptr(), 0, s), "f1"))
+                                                               rs1.data_ptr(), r1.data_ptr(), loss.data_ptr(), 0, None, s), "f1"))
             print(f"world=1 b={bb}: single-rank symmetric forward (+finalize) {t1:.4f} ms", flush=True)
 
 
