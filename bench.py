@@ -27,6 +27,7 @@ sample of the same workload.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -60,16 +61,25 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples SM clock, power and throttle reasons (NVML, ~10 ms period) while the timed region runs."""
+    """SM clock, power and throttle reasons while the timed region runs.  Preferred: the recipe's own
+    ``nvidia-smi --query-gpu=... -lms`` as a SEPARATE process (in-process NVML queries take the driver lock
+    from a second thread of the launching process: measured multi-millisecond stalls of the launch path at
+    N > 1); falls back to in-process NVML at a long period when nvidia-smi is absent."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=20):
         self.index = index
+        self.period_ms = period_ms
         self.samples = []
         self.stop_flag = threading.Event()
         self.thread = None
+        self.proc = None
         self.err = None
+        self.sm_max = None
 
     def _loop(self):
         try:
@@ -82,13 +92,24 @@ class ClockSampler:
                     rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
                     rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.samples.append((sm, pw, rs))
-                time.sleep(0.002)
+                self.samples.append((sm, pw, sorted(n for bit, n in self.REASONS.items() if rs & bit), time.time()))
+                time.sleep(0.2)
         except Exception as e:  # noqa: BLE001
             self.err = repr(e)
 
     def start(self):
-        try:  # NVML initialisation takes longer than a 20-step run: do it before the thread starts sampling
+        import shutil
+        exe = shutil.which("nvidia-smi")
+        if exe:
+            try:
+                self.proc = subprocess.Popen([exe, f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                              "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                return
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+                self.proc = None
+        try:
             import pynvml
             pynvml.nvmlInit()
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
@@ -99,19 +120,48 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._loop, daemon=True)
         self.thread.start()
 
+    def mark(self):
+        """the timed region starts now: samples before this instant are not 'under load'"""
+        self.t0 = time.time()
+
     def stop(self):
-        self.stop_flag.set()
-        if self.thread:
-            self.thread.join(timeout=2)
+        t1 = time.time()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+                out = ""
+            for ln in out.splitlines():
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    import datetime
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rs = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8])
+                          if v.lower().startswith("active")]
+                    self.samples.append((float(f[1]), float(f[3]), rs, ts))
+                    self.sm_max = float(f[2])
+                except ValueError:
+                    continue
+        else:
+            self.stop_flag.set()
+            if self.thread:
+                self.thread.join(timeout=2)
         if not self.samples:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=[f"no samples ({self.err})"])
+        inside = [x for x in self.samples if getattr(self, "t0", 0) <= x[3] <= t1 + 0.02]
+        total = len(self.samples)
+        if inside:
+            self.samples = inside
         sm = [x[0] for x in self.samples]
-        mask = 0
-        for x in self.samples:
-            mask |= x[2]
-        reasons = sorted(n for bit, n in self.REASONS.items() if mask & bit)
+        reasons = sorted({r for x in self.samples for r in x[2]})
         return dict(sm_mhz=statistics.median(sm), sm_min_mhz=min(sm), sm_max_mhz=self.sm_max,
-                    power_w_max=max(x[1] for x in self.samples), samples=len(sm), reasons=reasons)
+                    power_w_max=max(x[1] for x in self.samples), samples=len(sm), samples_total=total,
+                    inside_timed_region=bool(inside), reasons=reasons,
+                    how="nvidia-smi -lms %d (separate process)" % self.period_ms if self.proc is not None else "NVML thread, 200 ms")
 
 
 def run_reference(args, rank):
@@ -216,8 +266,8 @@ def main():
         """Which dataflow the public API takes for bb pairs per rank (decided at the first call per shape)."""
         if world == 1:
             return dict(gather_mode="single rank", sym_forward=bool(lib.maai_ntxent_fwd_is_symmetric(bb, 1, dp)))
-        key = ("usable", bb, dp, world, rank, str(dev), id(None))
-        peer = bool(P._peer_state.get(key))
+        # the same (cached, collectively voted) decision contrastive_loss takes at its first call with this shape
+        peer = bool(P.peer_gather_available() and P._peer_usable(bb, dp, world, rank, dev, None))
         if not peer:
             return dict(gather_mode="nccl all_gather_into_tensor", sym_forward=False)
         ws = P.PeerWorkspace.get(bb, dp, world, rank, dev, None)
@@ -302,16 +352,19 @@ def main():
         h1, h2 = make_inputs(bb)
         x = h1.requires_grad_(grad1)
         y = h2.requires_grad_(True)
+        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()  # a separate process: its start-up overlaps the warm-up steps
         for _ in range(warmup):
             step(x, y)
         barrier()
         _Profiler.reset()
         _Profiler.enabled = profile
-        sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
         if sampler:
-            sampler.start()
+            sampler.mark()
         launches0 = lib.maai_launch_count()
         evs = []
+        gc.disable()  # a collection pause on one rank is a stall of every rank
         for _ in range(steps):
             flush_buf.fill_(1)  # flush L2 between timed iterations (outside the event bracket)
             a = torch.cuda.Event(enable_timing=True)
@@ -321,6 +374,7 @@ def main():
             e.record()
             evs.append((a, e))
         barrier()
+        gc.enable()
         clocks = sampler.stop() if sampler else None
         _Profiler.enabled = False
         launches = lib.maai_launch_count() - launches0
@@ -331,8 +385,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             total_ms = float(t)
         spans = {k: [a.elapsed_time(e) for a, e in v] for k, v in _Profiler.events.items()}
+        if profile and world > 1:  # every rank's own view (stderr): a rank that waits for a peer shows it here
+            sys.stderr.write(f"[rank {rank}] step ms mean {sum(ms) / steps:.4f} median {statistics.median(ms):.4f} "
+                             f"max {max(ms):.4f}; spans " +
+                             json.dumps({k: round(statistics.mean(v), 4) for k, v in spans.items() if v}) + "\n")
         return dict(ms_per_step=total_ms / steps, ms_median=statistics.median(ms), launches=launches,
-                    spans=spans, loss=float(loss.detach()), clocks=clocks)
+                    spans=spans, loss=float(loss.detach()), clocks=clocks, ms_max=max(ms))
 
     def timed_graphed(bb, steps, warmup):
         """same step through maai_b200.GraphedNTXentLoss (forward and backward as one CUDA graph each)"""

@@ -482,7 +482,11 @@ class _NTXentFunction(torch.autograd.Function):
                 r_row = r_col[rank * 2 * b:(rank + 1) * 2 * b]
             ctx.save_for_backward(h1, h2, z_all, inv_norm, r_row, r_col, pos_cos, rowsum)
             ctx.cfg = (b, d, dp, dt, inv_tau, rank, world, full)
-            ctx.peer = (ws, i, ws.seq if (sync is not None and full) else 0)
+            bwd_flags = sync is not None and full
+            if bwd_flags and os.environ.get("MAAI_PEER_FLAGS_BWD", "1") == "0":  # A/B: barrier launch instead
+                ws.hdl.barrier(channel=1)
+                bwd_flags = False
+            ctx.peer = (ws, i, ws.seq if bwd_flags else 0)
             ctx.dz_acc = dz_acc
             ctx.acc_clean = True
         if stash is not None:

@@ -172,7 +172,7 @@ struct RankArgs {
   // multi-rank: producer-side waits on the peers' flags (null = ordered by the caller's barrier)
   const unsigned int* wait_flags = nullptr;
   unsigned int wait_seq = 0;
-  int wait_kind = 0, wait_slot_rows = 1, wait_my_slot = 0;
+  int wait_kind = 0, wait_slot_rows = 1, wait_my_slot = 0, wait_nslots = 1;
 };
 
 template <int D, bool BWD, int NQ, bool RANK = false, bool SYM = false>
@@ -196,6 +196,7 @@ int launch_tile(const void* q_base, int m_loc, const void* k_base, int m_glob, i
   p.wait_what = ra.wait_flags ? 1 : 0;
   p.wait_slot_rows = ra.wait_slot_rows;
   p.wait_my_slot = ra.wait_my_slot;
+  p.wait_nslots = ra.wait_nslots;
   p.m_loc = m_loc;
   p.m_glob = m_glob;
   p.row_global_base = row_global_base;
@@ -337,7 +338,8 @@ static int normalize_impl(const void* h1, const void* h2, int b, int d, int in_d
   if (zero_bytes && (!zero_fill || !aligned16(zero_fill) || (zero_bytes & 3)))
     return fail(MAAI_E_ARG, "zero_fill must be 16-byte aligned and zero_bytes a multiple of 4");
   const int wpb = 8;
-  const int grid = (b + wpb - 1) / wpb;
+  int grid = (b + wpb - 1) / wpb;
+  if (const int cap = sm_count() * 8; cap > 0 && grid > cap) grid = cap;  // one resident wave (8 CTAs of 256 per SM)
   const auto* pb = reinterpret_cast<const unsigned long long*>(peer_z_bases);
   const size_t esz = in_dtype == MAAI_DT_F32 ? 4 : 2;
   const int vec = dp / 32;
@@ -428,6 +430,7 @@ static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, f
     ra.wait_kind = maai::FLAG_Z;
     ra.wait_slot_rows = m_loc;
     ra.wait_my_slot = rank;
+    ra.wait_nslots = world;
   }
   const bool tail = prezeroed && !pos_rank && m_loc <= tail_finalize_rows();
   if (tail) {
@@ -555,6 +558,7 @@ static int launch_tile_groups(const void* z_glob, int b, int world, int rank, fl
     p.wait_what = 2;
     p.wait_slot_rows = m_loc;
     p.wait_my_slot = rank;
+    p.wait_nslots = world;
     p.grp_sync = to_sync(sync, world, rank);
   }
   const long long total = gp.total;
@@ -602,7 +606,8 @@ int maai_ntxent_normalize_chain(const void* h2, int b, int d, int in_dtype, cons
     return fail(MAAI_E_ARG, "zero_fill must be 16-byte aligned and zero_bytes a multiple of 4");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int wpb = 8;
-  const int grid = (b + wpb - 1) / wpb;
+  int grid = (b + wpb - 1) / wpb;
+  if (const int cap = sm_count() * 8; cap > 0 && grid > cap) grid = cap;
   const size_t esz = in_dtype == MAAI_DT_F32 ? 4 : 2;
   const int vec = dp / 32;
   const bool vec_ok = (d % vec) == 0 && (reinterpret_cast<uintptr_t>(h2) % (vec * esz)) == 0;
@@ -730,6 +735,7 @@ static int bwd_tiles_impl(const void* z_glob, const float* r_row, const float* r
     ra.wait_kind = maai::FLAG_R;
     ra.wait_slot_rows = m_loc;
     ra.wait_my_slot = rank;
+    ra.wait_nslots = world;
   }
   return dispatch_tile<true>(d_pad, q_base, rows, z_glob, m_glob, rank * m_loc + row_begin, inv_tau,
                              r_row + row_begin, r_col, nullptr, acc, b - row_begin, b, s, ra);

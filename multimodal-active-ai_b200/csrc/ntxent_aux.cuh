@@ -52,9 +52,12 @@ __device__ __forceinline__ void signal_peers(const PeerSync& s, int kind) {
 __device__ __forceinline__ void signal_when_grid_done(const PeerSync& s, int kind) {
   if (!s.peer_flags) return;
   __shared__ unsigned int is_last;
-  __threadfence_system();  // this thread's peer / multicast stores are performed before its CTA's ticket
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(s.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();  // every thread of the CTA has issued its peer / multicast stores ...
+  if (threadIdx.x == 0) {
+    __threadfence_system();  // ... and this fence is cumulative over what the barrier ordered before it (one
+                             // fence per CTA: 256 of them cost K1 10 us at 16384 pairs, profiles/r2_tuning_log.md)
+    is_last = (atomicAdd(s.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
   __syncthreads();
   if (is_last) {
     __threadfence_system();  // cumulativity: the other CTAs' fenced stores, observed through the counter
@@ -191,8 +194,6 @@ normalize_cast_kernel(const T* __restrict__ h1, const T* __restrict__ h2, int b,
                       unsigned long long mc_base, int world, int rank, float* __restrict__ inv_norm,
                       float* __restrict__ pos_cos, uint32_t* __restrict__ zero_fill, size_t zero_words,
                       const __grid_constant__ PeerSync sync) {
-  constexpr int DP = VEC * 32;
-  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   pdl_launch_dependents<1>();
   pdl_wait();
@@ -202,7 +203,11 @@ normalize_cast_kernel(const T* __restrict__ h1, const T* __restrict__ h2, int b,
     for (size_t i = tid; i < zero_words / 4; i += nth) p4[i] = make_uint4(0u, 0u, 0u, 0u);
     for (size_t i = (zero_words / 4) * 4 + tid; i < zero_words; i += nth) zero_fill[i] = 0u;
   }
-  if (k < b) normalize_pair<T, VEC>(h1, h2, b, d, vec_ok, z_local, peer_base, mc_base, world, rank, inv_norm, pos_cos, k, lane);
+  // pairs are strided over the grid's warps: the host caps the grid at one resident wave, so that with peer
+  // signalling every CTA pays the system-scope fence (an NVLink round trip) once, not once per 8 pairs
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  for (int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < b; k += nwarps)
+    normalize_pair<T, VEC>(h1, h2, b, d, vec_ok, z_local, peer_base, mc_base, world, rank, inv_norm, pos_cos, k, lane);
   signal_when_grid_done(sync, FLAG_Z);  // in-kernel replacement of the barrier launch behind the gather
 }
 
@@ -223,7 +228,6 @@ normalize_chain_kernel(const T* __restrict__ h2, int b, int d, bool vec_ok,
                        float* __restrict__ pos_cos, uint32_t* __restrict__ zero_fill, size_t zero_words,
                        const __grid_constant__ PeerSync sync) {
   constexpr int DP = VEC * 32;
-  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   pdl_launch_dependents<1>();
   pdl_wait();
@@ -233,7 +237,8 @@ normalize_chain_kernel(const T* __restrict__ h2, int b, int d, bool vec_ok,
     for (size_t i = tid; i < zero_words / 4; i += nth) p4[i] = make_uint4(0u, 0u, 0u, 0u);
     for (size_t i = (zero_words / 4) * 4 + tid; i < zero_words; i += nth) zero_fill[i] = 0u;
   }
-  if (k < b) {
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  for (int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < b; k += nwarps) {
   using Vec = typename std::conditional<VEC == 2, uint32_t, typename std::conditional<VEC == 4, uint2, uint4>::type>::type;
   float c[VEC];
   load_row_chunk<T, VEC>(h2 + (size_t)k * d, lane * VEC, d, vec_ok, c);

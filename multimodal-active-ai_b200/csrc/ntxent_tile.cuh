@@ -181,6 +181,7 @@ struct TileParams {
   int wait_what;       // 1: key tiles / r_col (rows of the gathered buffer), 2: anchor tiles of the GRP groups
   int wait_slot_rows;  // rows per rank slot (2b)
   int wait_my_slot;
+  int wait_nslots;     // rank slots (world)
   // GRP: the last CTA signals FLAG_L (this rank's staged partial sums are complete) through grp_sync
   PeerSync grp_sync;
 };
@@ -410,17 +411,29 @@ struct GrpWalk {
 };
 
 // TMA producer, multi-rank: wait until the rank slots that own global rows [row0, last] have signalled
-// (TileParams::wait_*); returns the updated "seen" mask.  Out of line: called a handful of times per CTA.
-__device__ __noinline__ uint32_t ensure_slots(const TileParams& p, uint32_t seen, int row0, int last) {
+// (TileParams::wait_*).  Out of line and called only when the producer enters a slot it has not checked: the
+// producer of the backward is latency-critical (a K stage lives ~NB + 1 tile periods, so the TMA prefetch runs
+// barely one tile ahead; a call with two integer divisions per tile cost 23 % -- profiles/r2_tuning_log.md).
+// st.seen: slots known to have landed (all ones once every slot has); [st.lo, st.hi): rows of the slot last
+// checked, inside which the caller's inline range test skips the call.
+struct SlotState {
+  uint32_t seen;
+  int lo, hi;
+};
+__device__ __noinline__ void ensure_slots(const TileParams& p, SlotState& st, int row0, int last) {
   bool waited = false;
-  for (int sl = row0 / p.wait_slot_rows; sl <= last / p.wait_slot_rows; ++sl)
-    if (!((seen >> sl) & 1u)) {
+  const int s_lo = row0 / p.wait_slot_rows, s_hi = last / p.wait_slot_rows;
+  for (int sl = s_lo; sl <= s_hi; ++sl)
+    if (!((st.seen >> sl) & 1u)) {
       wait_flag_ge(p.wait_flags + p.wait_kind * kFlagStride + sl, p.wait_seq);
-      seen |= 1u << sl;
+      st.seen |= 1u << sl;
       waited = true;
     }
   if (waited) fence_proxy_async_all();  // the TMA (async proxy) reads what the peers' stores wrote
-  return seen;
+  st.lo = s_hi * p.wait_slot_rows;
+  st.hi = st.lo + p.wait_slot_rows;
+  const uint32_t all = p.wait_nslots >= 32 ? 0xffffffffu : ((1u << p.wait_nslots) - 1u);
+  if ((st.seen & all) == all) st.seen = 0xffffffffu;
 }
 
 // Forward, last CTA done: every other CTA's sums are in L2 (their threads fenced before the CTA took its
@@ -534,10 +547,14 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       PROF_INIT();
       uint32_t t = 0, useg = 0;
       Walk walk(p);
-      // rank slots whose rows are known to have landed (in-kernel replacement of the gather barrier)
-      uint32_t seen = p.wait_flags ? (1u << p.wait_my_slot) : 0xffffffffu;
+      // rank slots whose rows are known to have landed (in-kernel replacement of the gather barrier); the
+      // inline test costs two compares per tile, the call happens once per slot change
+      SlotState slots{p.wait_flags ? (1u << p.wait_my_slot) : 0xffffffffu, 0, 0};
       auto ensure_rows = [&](int row0, int nrows, int limit) {
-        if (seen != 0xffffffffu) seen = ensure_slots(p, seen, row0, min(row0 + nrows, limit) - 1);
+        if (slots.seen == 0xffffffffu) return;
+        const int last = min(row0 + nrows, limit) - 1;
+        if (row0 >= slots.lo && last < slots.hi) return;
+        ensure_slots(p, slots, row0, last);
       };
       for (long long it = it_begin; it < it_end;) {
         int rb, j0, n;
