@@ -514,9 +514,23 @@ def main():
             sec = float(tt)
         return sec
 
+    def copies_only(steps):
+        """the H2D + D2H traffic of the e2e schedule without any compute: the PCIe / host-memory floor of e2e"""
+        dummy = torch.empty(2 * n_in + 1, device=dev)
+        for i in range(steps):
+            s_ = i & 1
+            with torch.cuda.stream(in_s):
+                d_in[s_].copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(out_s):
+                h_out[s_].copy_(dummy, non_blocking=True)
+        in_s.synchronize()
+        out_s.synchronize()
+
     for _ in range(args.warmup):
         e2e_serial_step()
     e2e_pipelined(args.warmup)
+    copies_only(args.warmup)
+    copy_floor_s = timed_e2e(copies_only)
     e2e_serial_s = timed_e2e(lambda k: [e2e_serial_step() for _ in range(k)])
     e2e_pipe_s = timed_e2e(e2e_pipelined)
     e2e_loss = float(h_out[(args.steps - 1) & 1][2 * n_in])
@@ -635,6 +649,9 @@ def main():
                     "ms_per_step": e2e_s / args.steps * 1e3,
                     "schedule": e2e_mode, "loss_read_on_host": e2e_loss,
                     "pipelined_ms_per_step": e2e_pipe_s / args.steps * 1e3,
+                    "copies_only_ms_per_step": copy_floor_s / args.steps * 1e3,
+                    "copies_only_note": "the same H2D + D2H bytes per step on the two copy streams with NO compute, all ranks "
+                                        "at once: the PCIe / host-memory floor of e2e on this box (e2e >= max(this, ms_per_step))",
                     "serial_value": B * args.steps / e2e_serial_s,
                     "serial_ms_per_step": e2e_serial_s / args.steps * 1e3,
                     "what": "every step: ONE pinned host buffer [h1|h2] -> device, contrastive_loss + backward, "

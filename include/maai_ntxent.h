@@ -73,6 +73,7 @@ int maai_ntxent_fwd_is_symmetric(int b, int world, int d_pad);
  *   local_flags      this rank's own flag block
  *   counter          one zero-initialised 32-bit device word of scratch (CTA-done counter, self-resetting)
  *   seq              step number: > 0, the same on every rank, larger at every step
+ *   timeout_s        wall-clock limit of a wait for a peer, seconds (0 = 300)
  * Buffer reuse stays the caller's business exactly as with barriers: a rank that has observed seq = t from a
  * peer knows that peer has enqueued, and its GPU executed, everything before its K1 of step t. */
 #define MAAI_FLAG_WORDS 96
@@ -81,6 +82,7 @@ typedef struct maai_peer_sync {
   unsigned int* local_flags;
   unsigned int* counter;
   unsigned int seq;
+  unsigned int timeout_s;
 } maai_peer_sync;
 
 /* Number of floats the `r_glob` array of maai_ntxent_bwd must hold: world*2b rounded up to 128. */

@@ -199,6 +199,8 @@ class PeerWorkspace:
         self.counter = self.raw[self.off_f + align(_lib.FLAG_WORDS * 4):][:4].view(torch.int32)
         # MAAI_PEER_FLAGS=0: order the fused gathers with symmetric-memory barrier launches instead (A/B runs)
         self.use_flags = os.environ.get("MAAI_PEER_FLAGS", "1") != "0"
+        # how long a kernel waits for a late peer before it traps (a dead rank must not hang the others forever)
+        self.timeout_s = int(os.environ.get("MAAI_PEER_TIMEOUT_S", "300"))
         self.seq = 0
         self.z = [self.raw[o:o + zb].view(torch.bfloat16).view(world, 2 * b, dp) for o in self.off_z]
         self.r = [self.raw[o:o + rb].view(torch.float32) for o in self.off_r]
@@ -254,7 +256,7 @@ class PeerWorkspace:
         """maai_peer_sync for step `seq` (None when barrier launches are used instead)."""
         if not self.use_flags:
             return None
-        return _lib.PeerSync(self.f_tab.data_ptr(), self.flags.data_ptr(), self.counter.data_ptr(), seq)
+        return _lib.PeerSync(self.f_tab.data_ptr(), self.flags.data_ptr(), self.counter.data_ptr(), seq, self.timeout_s)
 
     def backward_issued(self, i: int):
         self.bwd_pending[i] = False

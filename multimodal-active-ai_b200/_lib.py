@@ -22,7 +22,7 @@ FLAG_WORDS = 96
 class PeerSync(ctypes.Structure):
     """maai_peer_sync of include/maai_ntxent.h (host struct handed to the calls by pointer)."""
     _fields_ = [("peer_flag_bases", _c_void_p), ("local_flags", _c_void_p), ("counter", _c_void_p),
-                ("seq", ctypes.c_uint)]
+                ("seq", ctypes.c_uint), ("timeout_s", ctypes.c_uint)]
 
 
 _c_sync_p = ctypes.POINTER(PeerSync)

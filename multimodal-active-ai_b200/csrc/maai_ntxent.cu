@@ -150,6 +150,7 @@ maai::PeerSync to_sync(const maai_peer_sync* sy, int world, int rank) {
     s.seq = sy->seq;
     s.world = world;
     s.rank = rank;
+    s.timeout_s = sy->timeout_s;
   }
   return s;
 }
@@ -172,7 +173,8 @@ struct RankArgs {
   // multi-rank: producer-side waits on the peers' flags (null = ordered by the caller's barrier)
   const unsigned int* wait_flags = nullptr;
   unsigned int wait_seq = 0;
-  int wait_kind = 0, wait_slot_rows = 1, wait_my_slot = 0, wait_nslots = 1;
+  int wait_kind = 0, wait_my_slot = 0, wait_nslots = 1;
+  unsigned int wait_timeout_s = 0;
 };
 
 template <int D, bool BWD, int NQ, bool RANK = false, bool SYM = false>
@@ -193,10 +195,9 @@ int launch_tile(const void* q_base, int m_loc, const void* k_base, int m_glob, i
   p.wait_flags = ra.wait_flags;
   p.wait_seq = ra.wait_seq;
   p.wait_kind = ra.wait_kind;
-  p.wait_what = ra.wait_flags ? 1 : 0;
-  p.wait_slot_rows = ra.wait_slot_rows;
   p.wait_my_slot = ra.wait_my_slot;
   p.wait_nslots = ra.wait_nslots;
+  p.wait_timeout_s = ra.wait_timeout_s;
   p.m_loc = m_loc;
   p.m_glob = m_glob;
   p.row_global_base = row_global_base;
@@ -428,9 +429,9 @@ static int fwd_impl(const void* z_glob, int b, int world, int rank, int d_pad, f
     ra.wait_flags = sync->local_flags;
     ra.wait_seq = sync->seq;
     ra.wait_kind = maai::FLAG_Z;
-    ra.wait_slot_rows = m_loc;
     ra.wait_my_slot = rank;
     ra.wait_nslots = world;
+    ra.wait_timeout_s = sync->timeout_s;
   }
   const bool tail = prezeroed && !pos_rank && m_loc <= tail_finalize_rows();
   if (tail) {
@@ -555,10 +556,9 @@ static int launch_tile_groups(const void* z_glob, int b, int world, int rank, fl
     p.wait_flags = sync->local_flags;
     p.wait_seq = sync->seq;
     p.wait_kind = maai::FLAG_Z;
-    p.wait_what = 2;
-    p.wait_slot_rows = m_loc;
     p.wait_my_slot = rank;
     p.wait_nslots = world;
+    p.wait_timeout_s = sync->timeout_s;
     p.grp_sync = to_sync(sync, world, rank);
   }
   const long long total = gp.total;
@@ -733,9 +733,9 @@ static int bwd_tiles_impl(const void* z_glob, const float* r_row, const float* r
     ra.wait_flags = sync->local_flags;
     ra.wait_seq = sync->seq;
     ra.wait_kind = maai::FLAG_R;
-    ra.wait_slot_rows = m_loc;
     ra.wait_my_slot = rank;
     ra.wait_nslots = world;
+    ra.wait_timeout_s = sync->timeout_s;
   }
   return dispatch_tile<true>(d_pad, q_base, rows, z_glob, m_glob, rank * m_loc + row_begin, inv_tau,
                              r_row + row_begin, r_col, nullptr, acc, b - row_begin, b, s, ra);

@@ -40,7 +40,16 @@ struct PeerSync {
   unsigned int seq;
   int world;
   int rank;
+  unsigned int timeout_s;                // wall-clock limit of a wait for a peer (0 = 300 s)
 };
+// One lane per peer waits (in parallel) until that peer's word of kind `kind` has reached s.seq.  Call from a
+// full warp; follow with a CTA barrier before the other threads touch the peer-written data.
+__device__ __forceinline__ void wait_all_peers(const unsigned int* local_flags, int kind, unsigned int seq, int world,
+                                               int my_rank, unsigned int timeout_s) {
+  const int lane = threadIdx.x & 31;
+  if (lane < world && lane != my_rank) wait_flag_ge(local_flags + kind * kFlagStride + lane, seq, timeout_s);
+  __syncwarp();
+}
 // Called by threads 0 .. world-1 of ONE CTA after every store of this kernel has been fenced at system
 // scope and ordered before this point (per-thread __threadfence_system + CTA barrier + ticket counter).
 __device__ __forceinline__ void signal_peers(const PeerSync& s, int kind) {
@@ -366,8 +375,7 @@ finalize_loss_kernel(const __grid_constant__ FinalizeArgs f) {
   if (f.stage_tab && f.sync.peer_flags) {
     // cross-rank symmetric forward: the peers' staged partial sums (maai_ntxent_fwd_sym_tiles on THEIR GPUs)
     // must be complete before they are pulled: one waiting thread per peer, then the CTA barrier
-    if (int(threadIdx.x) < f.world && int(threadIdx.x) != f.my_rank)
-      wait_flag_ge(f.sync.local_flags + FLAG_L * kFlagStride + threadIdx.x, f.sync.seq);
+    if (threadIdx.x < 32) wait_all_peers(f.sync.local_flags, FLAG_L, f.sync.seq, f.world, f.my_rank, f.sync.timeout_s);
     __syncthreads();
   }
   const double acc = finalize_rows(f, rank * blockDim.x + threadIdx.x, kFinalizeCluster * blockDim.x);

@@ -171,17 +171,18 @@ struct TileParams {
   // done_ctr: zero-initialised 32-bit counter (K1's zero fill); null = no in-kernel finalize.
   unsigned int* done_ctr;
   FinalizeArgs fin;
-  // Multi-rank, optional (null = the caller ordered the gathers with a barrier launch): before the TMA
-  // producer first touches rows of rank slot s != wait_my_slot it waits until word [wait_kind][s] of this
-  // rank's flag block has reached wait_seq -- FWD: the peer's bf16 rows (FLAG_Z) for key tiles and, in the
-  // cross-rank symmetric forward, remote anchor tiles; BWD: the peer's row factors (FLAG_R) for r_col.
+  // Multi-rank, optional (null = the caller ordered the gathers with a barrier launch): right after its
+  // prologue the CTA waits until word [wait_kind][s] of this rank's flag block has reached wait_seq for every
+  // rank slot s != wait_my_slot -- FWD: the peers' bf16 rows (FLAG_Z), BWD: the peers' row factors (FLAG_R).
+  // The wait sits BEFORE the mbarrier pipeline starts on purpose: a peer may legitimately be seconds late
+  // (host stall on that rank), and the pipeline's own watchdog (mbar_wait, ~2 s) must only ever see waits
+  // that this CTA's warps resolve among themselves.
   const unsigned int* wait_flags;
   unsigned int wait_seq;
   int wait_kind;
-  int wait_what;       // 1: key tiles / r_col (rows of the gathered buffer), 2: anchor tiles of the GRP groups
-  int wait_slot_rows;  // rows per rank slot (2b)
   int wait_my_slot;
   int wait_nslots;     // rank slots (world)
+  unsigned int wait_timeout_s;
   // GRP: the last CTA signals FLAG_L (this rank's staged partial sums are complete) through grp_sync
   PeerSync grp_sync;
 };
@@ -410,32 +411,6 @@ struct GrpWalk {
   }
 };
 
-// TMA producer, multi-rank: wait until the rank slots that own global rows [row0, last] have signalled
-// (TileParams::wait_*).  Out of line and called only when the producer enters a slot it has not checked: the
-// producer of the backward is latency-critical (a K stage lives ~NB + 1 tile periods, so the TMA prefetch runs
-// barely one tile ahead; a call with two integer divisions per tile cost 23 % -- profiles/r2_tuning_log.md).
-// st.seen: slots known to have landed (all ones once every slot has); [st.lo, st.hi): rows of the slot last
-// checked, inside which the caller's inline range test skips the call.
-struct SlotState {
-  uint32_t seen;
-  int lo, hi;
-};
-__device__ __noinline__ void ensure_slots(const TileParams& p, SlotState& st, int row0, int last) {
-  bool waited = false;
-  const int s_lo = row0 / p.wait_slot_rows, s_hi = last / p.wait_slot_rows;
-  for (int sl = s_lo; sl <= s_hi; ++sl)
-    if (!((st.seen >> sl) & 1u)) {
-      wait_flag_ge(p.wait_flags + p.wait_kind * kFlagStride + sl, p.wait_seq);
-      st.seen |= 1u << sl;
-      waited = true;
-    }
-  if (waited) fence_proxy_async_all();  // the TMA (async proxy) reads what the peers' stores wrote
-  st.lo = s_hi * p.wait_slot_rows;
-  st.hi = st.lo + p.wait_slot_rows;
-  const uint32_t all = p.wait_nslots >= 32 ? 0xffffffffu : ((1u << p.wait_nslots) - 1u);
-  if ((st.seen & all) == all) st.seen = 0xffffffffu;
-}
-
 // Forward, last CTA done: every other CTA's sums are in L2 (their threads fenced before the CTA took its
 // ticket), so this CTA runs the per-row tail (finalize_rows) over all 2b rows.  Out of line on purpose: it
 // runs once per launch and must not cost the hot loops a register.  flag_smem / part_smem: shared-window
@@ -536,6 +511,11 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
   // memory: a grid whose threads skip the wait can complete before its predecessor has, and the
   // kernel after it would then see that predecessor's writes unordered (round 1's PDL failure).
   pdl_wait();
+  if (p.wait_flags) {  // in-kernel replacement of the barrier launch behind the fused gather (see TileParams)
+    if (warp == 0) wait_all_peers(p.wait_flags, p.wait_kind, p.wait_seq, p.wait_nslots, p.wait_my_slot, p.wait_timeout_s);
+    __syncthreads();
+    if (warp == 0 && lane == 0) fence_proxy_async_all();  // the TMA (async proxy) reads what the peers' stores wrote
+  }
   if (C::REGS_SM > 96) {
     if (warp < C::SM_WARP0) reg_dealloc<C::REGS_WG0>();
     else reg_alloc<C::REGS_SM>();
@@ -547,22 +527,11 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
       PROF_INIT();
       uint32_t t = 0, useg = 0;
       Walk walk(p);
-      // rank slots whose rows are known to have landed (in-kernel replacement of the gather barrier); the
-      // inline test costs two compares per tile, the call happens once per slot change
-      SlotState slots{p.wait_flags ? (1u << p.wait_my_slot) : 0xffffffffu, 0, 0};
-      auto ensure_rows = [&](int row0, int nrows, int limit) {
-        if (slots.seen == 0xffffffffu) return;
-        const int last = min(row0 + nrows, limit) - 1;
-        if (row0 >= slots.lo && last < slots.hi) return;
-        ensure_slots(p, slots, row0, last);
-      };
       for (long long it = it_begin; it < it_end;) {
         int rb, j0, n;
         walk.locate(it, it_end, rb, j0, n);
         mbar_wait(bar_q_empty, (useg & 1) ^ 1);
         PROF_MARK(0);
-        if (GRP && p.wait_what == 2)
-          ensure_rows(p.g_qrow0[walk.g] + rb * C::RB_ROWS, C::RB_ROWS, p.g_qrow0[walk.g] + p.g_rows[walk.g]);
         mbar_arrive_expect_tx(bar_q_full, NQ * C::TILE_BYTES);
 #pragma unroll
         for (int q = 0; q < NQ; ++q)
@@ -578,7 +547,6 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
             mbar_arrive(bar_k_full(st));
             continue;
           }
-          if (p.wait_what == 1) ensure_rows((j0 + jj) * C::KT, C::KT, p.m_glob);
           mbar_arrive_expect_tx(bar_k_full(st), C::TILE_BYTES + (BWD ? C::KT * 4 : 0));
 #pragma unroll
           for (int c = 0; c < C::CHUNKS; ++c)

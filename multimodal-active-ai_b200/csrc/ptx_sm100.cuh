@@ -45,7 +45,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // A producer rank signals "my stores of step `seq` have landed in your buffers" by a release store of
 // `seq` into ITS word of every peer's flag block (peer-mapped NVLink address); a consumer spins on its
 // LOCAL flag block with acquire loads until the word has reached `seq` (sequence numbers only grow, so
-// there is nothing to reset).  Bounded like mbar_wait: a protocol bug traps, it never hangs the GPU.
+// there is nothing to reset).
 __device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -56,20 +56,29 @@ __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p
 }
 // generic-proxy observations (the acquire above) before async-proxy reads (TMA loads of what the peer wrote)
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-// slow path out of line: the callers' hot loops must not pay registers / stack for the spin and its printf
-__device__ __noinline__ void wait_flag_spin(const unsigned int* flag, unsigned int seq) {
-  const long long t0 = clock64();
+// Waiting for a PEER is unbounded in principle (a rank may sit in a checkpoint or a data stall for many
+// seconds, exactly like a rank arriving late at an NCCL collective), so the timeout is a wall-clock one, long
+// (default 300 s, the caller's choice) and only a last resort against a dead rank: after it the kernel traps.
+// Slow path out of line: the callers' hot code must not pay registers / stack for the spin and its printf.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __noinline__ void wait_flag_spin(const unsigned int* flag, unsigned int seq, unsigned int timeout_s) {
+  const unsigned long long t0 = global_timer_ns();
+  const unsigned long long limit = (unsigned long long)(timeout_s ? timeout_s : 300u) * 1000000000ull;
   while (int(ld_acquire_sys_u32(flag) - seq) < 0) {
-    if (clock64() - t0 > 6000000000LL) {  // ~3 s: a peer that never signals (crashed rank, protocol bug)
-      printf("maai: peer flag wait timeout block %d thread %d flag %p want %u have %u\n", blockIdx.x, threadIdx.x,
-             (const void*)flag, seq, ld_acquire_sys_u32(flag));
+    if (global_timer_ns() - t0 > limit) {
+      printf("maai: peer flag wait timeout (%u s) block %d thread %d flag %p want %u have %u\n", timeout_s, blockIdx.x,
+             threadIdx.x, (const void*)flag, seq, ld_acquire_sys_u32(flag));
       __trap();
     }
-    __nanosleep(64);
+    __nanosleep(128);
   }
 }
-__device__ __forceinline__ void wait_flag_ge(const unsigned int* flag, unsigned int seq) {
-  if (int(ld_acquire_sys_u32(flag) - seq) < 0) wait_flag_spin(flag, seq);
+__device__ __forceinline__ void wait_flag_ge(const unsigned int* flag, unsigned int seq, unsigned int timeout_s) {
+  if (int(ld_acquire_sys_u32(flag) - seq) < 0) wait_flag_spin(flag, seq, timeout_s);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -70,10 +70,10 @@ def test_c_abi_argument_errors_without_gpu():
     assert lib.maai_ntxent_fwd_is_symmetric(4096, 1, 128) == 1 and lib.maai_ntxent_fwd_is_symmetric(4096, 2, 128) == 0
     assert lib.maai_ntxent_fwd_is_symmetric(2048, 1, 256) == 0 and lib.maai_ntxent_fwd_is_symmetric(8192, 1, 256) == 1
     # ABI v7: maai_peer_sync is validated on the host (null members, seq 0) before any CUDA call
-    bad = _lib.PeerSync(None, None, None, 1)
+    bad = _lib.PeerSync(None, None, None, 1, 0)
     assert lib.maai_ntxent_fwd(ptr, 4, 2, 0, 64, 1.0, ptr, ptr, None, ptr, 0, ctypes.byref(bad), None) == _lib.E_ARG
     assert b"maai_peer_sync" in lib.maai_last_error()
-    bad = _lib.PeerSync(ptr.value, ptr.value, ptr.value, 0)
+    bad = _lib.PeerSync(ptr.value, ptr.value, ptr.value, 0, 0)
     assert lib.maai_ntxent_bwd(ptr, ptr, ptr, 1, ptr, ptr, ptr, ptr, 0, ptr, ptr, 4, 2, 0, 8, 64, 1.0, 3, ptr, ptr, ptr, 0,
                                ctypes.byref(bad), None) == _lib.E_ARG
     with pytest.raises(ValueError):

@@ -261,7 +261,7 @@ def test_emulated_ranks_inkernel_flags(world, b, d, tau, sym):
         H1 = torch.randn(world * b, d, generator=g)
         H2 = H1 + 0.5 * torch.randn(world * b, d, generator=g)
         h = [(H1[p * b:(p + 1) * b].contiguous().to(dev), H2[p * b:(p + 1) * b].contiguous().to(dev)) for p in range(world)]
-        sync = [_lib.PeerSync(f_tab.data_ptr(), flags[p].data_ptr(), ctr[p].data_ptr(), seq) for p in range(world)]
+        sync = [_lib.PeerSync(f_tab.data_ptr(), flags[p].data_ptr(), ctr[p].data_ptr(), seq, 5) for p in range(world)]
         inv = torch.zeros(world, 2 * b, device=dev); cos = torch.zeros(world, b, device=dev)
         wsb = lib.maai_ntxent_workspace_bytes(b, dp, 1) // 4
         head = (2 * b + _lib.WS_CTL_WORDS + 127) // 128 * 128
