@@ -56,6 +56,16 @@ EncodeTiledFn get_encode() {
 int make_rows_tmap(CUtensorMap* m, const void* base, int rows, int d_pad) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(MAAI_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs the device's primary context current on THIS thread.
+  // A thread that has only used cached allocations so far (the autograd engine's device thread running the
+  // C++ binding's backward) may not have one bound yet -> CUDA_ERROR_INVALID_CONTEXT (201).  One runtime
+  // call per (thread, device) binds it.
+  static thread_local int ctx_bound_dev = -1;
+  int dev = -1;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev != ctx_bound_dev) {
+    cudaFree(nullptr);
+    ctx_bound_dev = dev;
+  }
   cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
   cuuint32_t box[2] = {64, 128};
