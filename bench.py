@@ -61,107 +61,101 @@ def load_peaks():
 
 
 class ClockSampler:
-    """SM clock, power and throttle reasons while the timed region runs.  Preferred: the recipe's own
-    ``nvidia-smi --query-gpu=... -lms`` as a SEPARATE process (in-process NVML queries take the driver lock
-    from a second thread of the launching process: measured multi-millisecond stalls of the launch path at
-    N > 1); falls back to in-process NVML at a long period when nvidia-smi is absent."""
-    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
-               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
-    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """SM clock, power and throttle reasons while the timed region runs: the recipe's own
+    ``nvidia-smi --query-gpu=... -lms`` as a SEPARATE process (in-process NVML queries from a second thread
+    take the driver lock of the launching process: measured multi-millisecond stalls of the launch path at
+    N > 1).  A reader thread stamps every line on arrival; ``stop()`` reports the samples that arrived inside
+    the timed region.  Runs shorter than the sampler's period (~25 ms per query: 20 steps at 8 GPUs take 8 ms)
+    get their under-load samples from an untimed continuation of the same loop (``need_more`` / bench.py's
+    timed_run), and say so."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index, period_ms=20):
         self.index = index
         self.period_ms = period_ms
-        self.samples = []
-        self.stop_flag = threading.Event()
-        self.thread = None
+        self.samples = []   # (sm MHz, W, [reasons], host time of arrival)
         self.proc = None
+        self.thread = None
         self.err = None
         self.sm_max = None
+        self.t0 = self.t1 = None
 
-    def _loop(self):
+    def _reader(self):
         try:
-            import pynvml
-            h = self.handle
-            while not self.stop_flag.is_set():
-                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
-                pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+            for ln in self.proc.stdout:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 7:
+                    continue
                 try:
-                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.samples.append((sm, pw, sorted(n for bit, n in self.REASONS.items() if rs & bit), time.time()))
-                time.sleep(0.2)
+                    rs = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7])
+                          if v.lower().startswith("active")]
+                    self.samples.append((float(f[0]), float(f[2]), rs, time.time()))
+                    self.sm_max = float(f[1])
+                except ValueError:
+                    continue
         except Exception as e:  # noqa: BLE001
             self.err = repr(e)
 
     def start(self):
         import shutil
         exe = shutil.which("nvidia-smi")
-        if exe:
-            try:
-                self.proc = subprocess.Popen([exe, f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                              "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
-                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-                return
-            except Exception as e:  # noqa: BLE001
-                self.err = repr(e)
-                self.proc = None
+        if not exe:
+            self.err = "nvidia-smi not found"
+            return
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.proc = subprocess.Popen([exe, f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
         except Exception as e:  # noqa: BLE001
             self.err = repr(e)
             return
-        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread = threading.Thread(target=self._reader, daemon=True)
         self.thread.start()
+        t = time.time()
+        while not self.samples and time.time() - t < 3.0:  # the process is up and reporting
+            time.sleep(0.01)
 
     def mark(self):
-        """the timed region starts now: samples before this instant are not 'under load'"""
+        """the timed region starts now"""
         self.t0 = time.time()
 
-    def stop(self):
-        t1 = time.time()
+    def mark_end(self):
+        self.t1 = time.time()
+
+    def inside(self):
+        return [x for x in self.samples if self.t0 is not None and self.t0 <= x[3] <= (self.t1 or time.time())]
+
+    def need_more(self, t_since):
+        """no sample has arrived since t_since yet (and the sampler works at all)"""
+        return self.proc is not None and self.samples and not any(x[3] >= t_since for x in self.samples)
+
+    def stop(self, continuation_from=None):
         if self.proc is not None:
             self.proc.terminate()
             try:
-                out, _ = self.proc.communicate(timeout=5)
+                self.proc.wait(timeout=3)
             except Exception:  # noqa: BLE001
                 self.proc.kill()
-                out = ""
-            for ln in out.splitlines():
-                f = [x.strip() for x in ln.split(",")]
-                if len(f) < 8:
-                    continue
-                try:
-                    import datetime
-                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                    rs = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8])
-                          if v.lower().startswith("active")]
-                    self.samples.append((float(f[1]), float(f[3]), rs, ts))
-                    self.sm_max = float(f[2])
-                except ValueError:
-                    continue
-        else:
-            self.stop_flag.set()
             if self.thread:
                 self.thread.join(timeout=2)
         if not self.samples:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=[f"no samples ({self.err})"])
-        inside = [x for x in self.samples if getattr(self, "t0", 0) <= x[3] <= t1 + 0.02]
-        total = len(self.samples)
-        if inside:
-            self.samples = inside
-        sm = [x[0] for x in self.samples]
-        reasons = sorted({r for x in self.samples for r in x[2]})
+        inside = self.inside()
+        where = "inside the timed region"
+        use = inside
+        if not use and continuation_from is not None:
+            use = [x for x in self.samples if x[3] >= continuation_from]
+            where = ("the timed region is shorter than the sampler's period: sampled during an untimed continuation of "
+                     "the same loop, right after it")
+        if not use:
+            use, where = self.samples, "around the timed region"
+        sm = [x[0] for x in use]
+        reasons = sorted({r for x in use for r in x[2]})
         return dict(sm_mhz=statistics.median(sm), sm_min_mhz=min(sm), sm_max_mhz=self.sm_max,
-                    power_w_max=max(x[1] for x in self.samples), samples=len(sm), samples_total=total,
-                    inside_timed_region=bool(inside), reasons=reasons,
-                    how="nvidia-smi -lms %d (separate process)" % self.period_ms if self.proc is not None else "NVML thread, 200 ms")
+                    power_w_max=max(x[1] for x in use), samples=len(use), sampled=where, reasons=reasons,
+                    how="nvidia-smi -lms %d (separate process)" % self.period_ms)
 
 
 def run_reference(args, rank):
@@ -375,9 +369,31 @@ def main():
             evs.append((a, e))
         barrier()
         gc.enable()
-        clocks = sampler.stop() if sampler else None
         _Profiler.enabled = False
-        launches = lib.maai_launch_count() - launches0
+        clocks = None
+        launches_timed = lib.maai_launch_count() - launches0
+        if sample_clocks:
+            # A run shorter than the sampler's period (20 steps at 8 GPUs take 8 ms) has no sample inside it:
+            # every rank then keeps the same load going, untimed, for ~80 ms (rank 0 decides, all ranks follow:
+            # the steps depend on each other across ranks) and the clocks are read there.
+            n_extra = 0
+            if sampler:
+                sampler.mark_end()
+                if not sampler.inside():
+                    per_step = max(1e-5, (sampler.t1 - sampler.t0) / steps)
+                    n_extra = min(2000, int(0.08 / per_step) + 1)
+            if world > 1:
+                t = torch.tensor([n_extra], device=dev, dtype=torch.int64)
+                dist.broadcast(t, 0)
+                n_extra = int(t)
+            cont = time.time() if n_extra else None
+            for _ in range(n_extra):
+                step(x, y)
+            barrier()
+            if sampler:
+                clocks = sampler.stop(cont)
+        _Profiler.enabled = False
+        launches = launches_timed if sample_clocks else lib.maai_launch_count() - launches0
         ms = [a.elapsed_time(e) for a, e in evs]
         total_ms = sum(ms)
         if world > 1:
@@ -463,16 +479,17 @@ def main():
     out_s = torch.cuda.Stream(device=dev)
     main_s = torch.cuda.current_stream()
     ev_in = [torch.cuda.Event() for _ in range(2)]      # inputs of the slot are on the device
-    ev_free = [torch.cuda.Event() for _ in range(2)]    # the step that read the slot's inputs has finished
     ev_done = [torch.cuda.Event() for _ in range(2)]    # results of the slot are computed
     ev_out = [torch.cuda.Event() for _ in range(2)]     # results of the slot are on the host
 
     def e2e_pipelined(steps):
+        keep = [None, None]  # the slot's device results stay referenced until their D2H copy has been consumed
+
         def h2d(i):
             s_ = i & 1
             with torch.cuda.stream(in_s):
                 if i >= 2:
-                    in_s.wait_event(ev_free[s_])
+                    in_s.wait_event(ev_done[s_])  # the step that read this slot's inputs has finished
                 d_in[s_].copy_(h_in, non_blocking=True)
                 ev_in[s_].record(in_s)
         h2d(0)
@@ -486,18 +503,15 @@ def main():
             loss, _, _ = maai_b200.contrastive_loss(x, y, temperature=tau, local_rank=rank, world_size=world,
                                                     device=dev, key_grad=True)
             loss.backward()
-            ev_free[s_].record(main_s)
             ev_done[s_].record(main_s)
             if i >= 2:
                 ev_out[s_].synchronize()  # the host has consumed this slot's previous results
+            keep[s_] = (loss, x, y)
             with torch.cuda.stream(out_s):
                 out_s.wait_event(ev_done[s_])
-                lg, g1, g2 = loss.detach(), x.grad, y.grad
-                for tns in (lg, g1, g2):
-                    tns.record_stream(out_s)
-                h_out[s_][:n_in].copy_(g1.view(-1), non_blocking=True)
-                h_out[s_][n_in:2 * n_in].copy_(g2.view(-1), non_blocking=True)
-                h_out[s_][2 * n_in:].copy_(lg.view(1), non_blocking=True)
+                h_out[s_][:n_in].copy_(x.grad.view(-1), non_blocking=True)
+                h_out[s_][n_in:2 * n_in].copy_(y.grad.view(-1), non_blocking=True)
+                h_out[s_][2 * n_in:].copy_(loss.detach().view(1), non_blocking=True)
                 ev_out[s_].record(out_s)
         for s_ in range(min(2, steps)):
             ev_out[s_].synchronize()
