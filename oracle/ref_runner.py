@@ -35,6 +35,36 @@ def load_reference():
     return mod
 
 
+_REF = None
+
+
+def reference_loss(hidden1, hidden2, temperature, rank=0, world=1):
+    """The reference's loss value (autograd-connected) for harnesses that compare whole training steps
+    (tools/simclr_step.py, tools/convergence_parity.py): the unmodified reference file when the build-time
+    copy exists -- its own ``dist.all_gather`` branch for world > 1 -- else the torch port of this package
+    (keys gathered with ``dist.all_gather`` like the reference does).  The ONE place outside tests where the
+    reference's formulation is spelled out is oracle/ntxent_torch_port.py."""
+    global _REF
+    if _REF is None:
+        _REF = load_reference() or False
+    h1, h2 = hidden1.float(), hidden2.float()
+    if _REF:
+        return _REF.contrastive_loss(h1, h2, temperature=temperature, local_rank=rank, world_size=world,
+                                     device=h1.device)[0]
+    from .ntxent_torch_port import ntxent_port
+    if world == 1:
+        return ntxent_port(h1, h2, temperature)
+    import torch.distributed as dist
+
+    def gather(t):
+        outs = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        return torch.cat(outs, 0)
+    k1 = gather(torch.nn.functional.normalize(h1.detach(), dim=1))
+    k2 = gather(torch.nn.functional.normalize(h2.detach(), dim=1))
+    return ntxent_port(h1, h2, temperature, keys1=k1, keys2=k2, rank=rank)
+
+
 class _LocalGather:
     """Stand-in for torch.distributed inside the reference module: all_gather(list, tensor) fills the list
     with the chunks of pre-normalised keys (alternating view a / view b, the order of Objective.py:52-53)."""

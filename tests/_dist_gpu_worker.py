@@ -118,6 +118,44 @@ def main():
         if rank == 0:
             print("fourth forward in flight raised:", raised)
         ok = ok and raised
+    # ---- world > 1 convergence parity of the DEFAULT gradient semantics: a small encoder trained for
+    # 40 SGD steps (a) on W ranks with the fused loss, key_grad=True, parameter gradients averaged over the ranks
+    # as DDP does, and (b) in a single process on the concatenated batch with the reference's own formulation
+    # (oracle/ref_runner.reference_loss: the unmodified file when present).  Same initial weights, same data:
+    # the mean of the rank losses must follow the reference's loss curve and the weights must end up together.
+    from oracle.ref_runner import reference_loss
+    b, din, dout, tau, steps, lr = 256, 48, 32, 0.2, 40, 0.5
+
+    def make_net():
+        torch.manual_seed(7)
+        return torch.nn.Sequential(torch.nn.Linear(din, 96), torch.nn.ReLU(), torch.nn.Linear(96, dout)).to(dev)
+
+    g = torch.Generator().manual_seed(11)
+    X1 = torch.randn(steps, world * b, din, generator=g)
+    X2 = X1 + 0.4 * torch.randn(steps, world * b, din, generator=g)
+    net_f, net_r = make_net(), make_net()
+    opt_f = torch.optim.SGD(net_f.parameters(), lr=lr)
+    opt_r = torch.optim.SGD(net_r.parameters(), lr=lr)
+    curve_f, curve_r = [], []
+    for t in range(steps):
+        xa = X1[t, rank * b:(rank + 1) * b].to(dev); xb = X2[t, rank * b:(rank + 1) * b].to(dev)
+        loss = maai_b200.contrastive_loss(net_f(xa), net_f(xb), temperature=tau, local_rank=rank, world_size=world,
+                                          device=dev, key_grad=True)[0]
+        opt_f.zero_grad(); loss.backward()
+        for prm in net_f.parameters():
+            dist.all_reduce(prm.grad); prm.grad /= world        # DDP's gradient averaging
+        opt_f.step()
+        lm = loss.detach().clone(); dist.all_reduce(lm); curve_f.append(float(lm) / world)
+        lr_ = reference_loss(net_r(X1[t].to(dev)), net_r(X2[t].to(dev)), tau)   # single process, global batch
+        opt_r.zero_grad(); lr_.backward(); opt_r.step()
+        curve_r.append(float(lr_.detach()))
+    curve_f, curve_r = np.array(curve_f), np.array(curve_r)
+    dcurve = float(np.abs(curve_f - curve_r).max() / np.abs(curve_r).max())
+    dw = max(float((pf - pr).norm() / pr.norm()) for pf, pr in zip(net_f.parameters(), net_r.parameters()))
+    if rank == 0:
+        print(f"convergence parity, default full gradient + DDP averaging vs single-process reference on the global batch: "
+              f"loss {curve_r[0]:.4f} -> {curve_r[-1]:.4f}, max curve diff {dcurve:.2e}, max weight diff {dw:.2e}")
+    ok = ok and dcurve <= 5e-3 and dw <= 2e-2
     # ---- chained views across ranks (NTXentLoss(chain_views=True)): half the gather payload, same results
     for peer in ([False, True] if peer_gather_available() else [False]):
         b, d, tau = 320, 128, 0.4

@@ -21,25 +21,12 @@ import torch.nn.functional as F
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-LARGE_NUM = 1e9
+from oracle.ref_runner import reference_loss  # noqa: E402  (the unmodified reference file, or the one torch port)
 
 
 def reference_formulation(hidden1, hidden2, temperature):
-    """Objective.py:41-79, world_size == 1 branch, op for op in fp32."""
-    hidden1 = F.normalize(hidden1.float(), dim=1, p=2)
-    hidden2 = F.normalize(hidden2.float(), dim=1, p=2)
-    b = hidden1.shape[0]
-    idx = torch.arange(b, device=hidden1.device)
-    labels = F.one_hot(idx, b * 2).float()
-    masks = F.one_hot(idx, b).float()
-    aa = hidden1 @ hidden1.t() / temperature - masks * LARGE_NUM
-    bb = hidden2 @ hidden2.t() / temperature - masks * LARGE_NUM
-    ab = hidden1 @ hidden2.t() / temperature
-    ba = hidden2 @ hidden1.t() / temperature
-
-    def ce(t, x):
-        return -(t * F.log_softmax(x, dim=1)).sum() / x.shape[0]
-    return ce(labels, torch.cat([ab, aa], 1)) + ce(labels, torch.cat([ba, bb], 1))
+    """Objective.py:41-79, world_size == 1 branch, as the reference executes it."""
+    return reference_loss(hidden1, hidden2, temperature)
 
 
 def lr_at(step, base_lr, warmup, total):

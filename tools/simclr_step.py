@@ -31,35 +31,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import maai_b200  # noqa: E402
 
-LARGE_NUM = 1e9
+from oracle.ref_runner import reference_loss  # noqa: E402  (the unmodified reference file, or the one torch port)
 
 
 def reference_formulation(hidden1, hidden2, temperature, rank, world):
-    """Objective.py:41-79 op for op (fp32, int64 one-hots built on the host then moved, 4 matmuls)."""
-    hidden1 = F.normalize(hidden1.float(), dim=1, p=2)
-    hidden2 = F.normalize(hidden2.float(), dim=1, p=2)
-    b = hidden1.shape[0]
-    if world > 1:
-        def gather(t):
-            outs = [torch.zeros_like(t) for _ in range(world)]
-            dist.all_gather(outs, t)
-            return torch.cat(outs, 0)
-        h1l, h2l = gather(hidden1), gather(hidden2)
-        idx = torch.tensor(range(b)) + rank * b
-    else:
-        h1l, h2l = hidden1, hidden2
-        idx = torch.tensor(range(b))
-    B = h1l.shape[0]
-    labels = F.one_hot(idx, B * 2).to(hidden1.device)
-    masks = F.one_hot(idx, B).to(hidden1.device)
-    aa = torch.matmul(hidden1, h1l.t()) / temperature - masks * LARGE_NUM
-    bb = torch.matmul(hidden2, h2l.t()) / temperature - masks * LARGE_NUM
-    ab = torch.matmul(hidden1, h2l.t()) / temperature
-    ba = torch.matmul(hidden2, h1l.t()) / temperature
-
-    def ce(t, x):
-        return -(t * F.log_softmax(x, dim=1)).sum() / x.shape[0]
-    return ce(labels, torch.cat([ab, aa], 1)) + ce(labels, torch.cat([ba, bb], 1))
+    """Objective.py:41-79 as the reference executes it (fp32, int64 one-hots built on the host then moved, 4 matmuls,
+    its own dist.all_gather for world > 1)."""
+    return reference_loss(hidden1, hidden2, temperature, rank, world)
 
 
 class MLP(torch.nn.Module):
