@@ -359,6 +359,7 @@ def main():
         launches0 = lib.maai_launch_count()
         evs = []
         gc.disable()  # a collection pause on one rank is a stall of every rank
+        t_host = time.perf_counter()
         for _ in range(steps):
             flush_buf.fill_(1)  # flush L2 between timed iterations (outside the event bracket)
             a = torch.cuda.Event(enable_timing=True)
@@ -367,6 +368,7 @@ def main():
             loss = step(x, y)
             e.record()
             evs.append((a, e))
+        host_issue_ms = (time.perf_counter() - t_host) * 1e3 / steps  # how fast this rank's host enqueues a step
         barrier()
         gc.enable()
         _Profiler.enabled = False
@@ -406,7 +408,7 @@ def main():
                              f"max {max(ms):.4f}; spans " +
                              json.dumps({k: round(statistics.mean(v), 4) for k, v in spans.items() if v}) + "\n")
         return dict(ms_per_step=total_ms / steps, ms_median=statistics.median(ms), launches=launches,
-                    spans=spans, loss=float(loss.detach()), clocks=clocks, ms_max=max(ms))
+                    spans=spans, loss=float(loss.detach()), clocks=clocks, ms_max=max(ms), host_issue_ms=host_issue_ms)
 
     def timed_graphed(bb, steps, warmup):
         """same step through maai_b200.GraphedNTXentLoss (forward and backward as one CUDA graph each)"""
@@ -482,8 +484,11 @@ def main():
     ev_done = [torch.cuda.Event() for _ in range(2)]    # results of the slot are computed
     ev_out = [torch.cuda.Event() for _ in range(2)]     # results of the slot are on the host
 
+    e2e_host = {}
+
     def e2e_pipelined(steps):
         keep = [None, None]  # the slot's device results stay referenced until their D2H copy has been consumed
+        e2e_host["t0"] = time.perf_counter()
 
         def h2d(i):
             s_ = i & 1
@@ -513,6 +518,7 @@ def main():
                 h_out[s_][n_in:2 * n_in].copy_(y.grad.view(-1), non_blocking=True)
                 h_out[s_][2 * n_in:].copy_(loss.detach().view(1), non_blocking=True)
                 ev_out[s_].record(out_s)
+        e2e_host["issue_s"] = time.perf_counter() - e2e_host["t0"]
         for s_ in range(min(2, steps)):
             ev_out[s_].synchronize()
 
@@ -647,7 +653,8 @@ def main():
                        "step_frac_bf16_peak": step_tflops / peaks["bf16"],
                        # executed flops: the symmetric forward runs half the forward's MMAs
                        "step_tflops_per_gpu_executed": step_tflops * ((20.0 / 24.0) if used["sym_forward"] else 1.0),
-                       "ms_median": main_r["ms_median"], "loss": main_r["loss"],
+                       "ms_median": main_r["ms_median"], "ms_max": main_r["ms_max"], "loss": main_r["loss"],
+                       "host_issue_ms_per_step": main_r["host_issue_ms"],
                        "fwd_call_ms": fwd_ms, "bwd_call_ms": bwd_ms,
                        "span_ms_mean": {k: (statistics.mean(v) if v else None) for k, v in main_r["spans"].items()},
                        "run_lengths": {
@@ -663,6 +670,7 @@ def main():
                     "ms_per_step": e2e_s / args.steps * 1e3,
                     "schedule": e2e_mode, "loss_read_on_host": e2e_loss,
                     "pipelined_ms_per_step": e2e_pipe_s / args.steps * 1e3,
+                    "pipelined_host_issue_ms_per_step": e2e_host.get("issue_s", 0.0) / args.steps * 1e3,
                     "copies_only_ms_per_step": copy_floor_s / args.steps * 1e3,
                     "copies_only_note": "the same H2D + D2H bytes per step on the two copy streams with NO compute, all ranks "
                                         "at once: the PCIe / host-memory floor of e2e on this box (e2e >= max(this, ms_per_step))",

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MAAI_ABI_VERSION 7
+#define MAAI_ABI_VERSION 8
 
 #define MAAI_OK 0
 #define MAAI_E_ARG (-1)
@@ -177,6 +177,20 @@ int maai_ntxent_fwd_sym_finalize(float* rowsum_l, const void* const* stage_bases
                                  const void* const* peer_r_bases, void* mc_r_base, float* loss_out,
                                  const maai_peer_sync* sync /* wait kind 2 of every peer, signal kind 1 */,
                                  void* stream);
+
+/* The cross-rank symmetric forward in ONE launch (needs the in-kernel synchronisation, sync != NULL): instead of
+ * staging the partial row sums it computed for the other ranks' anchors, the tile kernel adds them straight into
+ * the OWNERS' row sums over NVLink (red.add through peer-mapped addresses), its last CTA signals kind 2, waits
+ * for every peer's kind-2 signal (then this rank's row sums are complete) and runs the per-row tail itself:
+ * no staging vectors, no zero launch for them, no finalize launch, no pull.
+ *   rowsum_l          this rank's row sums: base of a step workspace IN PEER-MAPPED memory, zero-filled by K1
+ *                     (the peers add into it once they have observed this rank's kind-0 signal, i.e. after K1)
+ *   peer_rowsum_host  HOST array of `world` device pointers: rank p's rowsum_l as mapped into this process
+ *   r_out / peer_r_bases / mc_r_base / loss_out   as in maai_ntxent_fwd_peer */
+int maai_ntxent_fwd_sym_direct(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
+                               const float* pos_cos, float* rowsum_l, const void* const* peer_rowsum_host,
+                               float* r_out, const void* const* peer_r_bases, void* mc_r_base, float* loss_out,
+                               const maai_peer_sync* sync, void* stream);
 
 /* K2 for validate() (Contrastive_Learning.py:860-868): the same forward plus, for every view-a anchor
  * k of this rank, pos_rank[k] = number of view-b keys of ALL ranks whose similarity to the anchor is

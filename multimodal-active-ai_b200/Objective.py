@@ -184,7 +184,12 @@ class PeerWorkspace:
         self.off_s = [self.NBUF * (align(zb) + align(rb)) + i * align(sb) for i in range(self.NBUF)]
         # flag block of the in-kernel peer synchronisation (maai_peer_sync) + one counter word
         self.off_f = self.NBUF * (align(zb) + align(rb) + align(sb))
-        total = self.off_f + align(_lib.FLAG_WORDS * 4) + 256
+        # step workspaces (row sums | control words | dz accumulator) in peer-mapped memory: in the one-launch
+        # cross-rank symmetric forward the peers add their partial row sums straight into the owner's
+        wb = lib.maai_ntxent_workspace_bytes(b, dp, 1)
+        self.wb = wb
+        self.off_w = [self.off_f + align(_lib.FLAG_WORDS * 4) + 256 + i * align(wb) for i in range(self.NBUF)]
+        total = self.off_w[-1] + align(wb)
         self.raw = symm_mem.empty((total,), dtype=torch.uint8, device=device)
         self.raw.zero_()                                 # r padding must read as zero
         self.hdl = symm_mem.rendezvous(self.raw, group if group is not None else dist.group.WORLD)
@@ -195,6 +200,9 @@ class PeerWorkspace:
         self.s_tab = [tab(o) for o in self.off_s]
         self.stage = [self.raw[o:o + sb].view(torch.float32) for o in self.off_s]
         self.f_tab = tab(self.off_f)
+        self.wsbuf = [self.raw[o:o + wb].view(torch.float32) for o in self.off_w]
+        self.w_host = [(ctypes.c_void_p * world)(*[p + o for p in ptrs]) for o in self.off_w]  # HOST arrays of peer addresses
+        self.head = (2 * b + _lib.WS_CTL_WORDS + 127) // 128 * 128
         self.flags = self.raw[self.off_f:self.off_f + _lib.FLAG_WORDS * 4].view(torch.int32)
         self.counter = self.raw[self.off_f + align(_lib.FLAG_WORDS * 4):][:4].view(torch.int32)
         # MAAI_PEER_FLAGS=0: order the fused gathers with symmetric-memory barrier launches instead (A/B runs)
@@ -418,7 +426,13 @@ class _NTXentFunction(torch.autograd.Function):
         sync = ws.sync_for(ws.seq)   # ctypes struct (kept alive until the calls below have returned) or None
         psync = ctypes.byref(sync) if sync is not None else None
         z_all = ws.z[i]
-        wsp, rowsum, dz_acc = _step_workspace(lib, b, dp, needs_grad, dev)
+        direct = sync is not None and _sym_forward_enabled(b, dp, world) and os.environ.get("MAAI_SYM_DIRECT", "1") != "0"
+        if direct:  # the peers add into this rank's row sums: the step workspace lives in the symmetric allocation
+            wsp = ws.wsbuf[i]
+            rowsum = wsp[:2 * b]
+            dz_acc = wsp[ws.head:ws.head + 2 * b * dp].view(2 * b, dp) if needs_grad else None
+        else:
+            wsp, rowsum, dz_acc = _step_workspace(lib, b, dp, needs_grad, dev)
         small = torch.empty(3 * b + 4, dtype=torch.float32, device=dev)
         inv_norm = small[:2 * b]
         pos_cos = small[2 * b:3 * b]
@@ -447,10 +461,20 @@ class _NTXentFunction(torch.autograd.Function):
         if not peer_r and needs_grad:  # keys detached (reference semantics): local row factors only, r_col = 0
             r_row = torch.empty(2 * b, dtype=torch.float32, device=dev)
             r_col = torch.zeros(ws.r_len, dtype=torch.float32, device=dev)
-        if _sym_forward_enabled(b, dp, world):
-            # every pair of rank slots is computed once: own block + the anchors of the ranks ahead on
-            # the ring against the local keys; the other half of each row sum arrives through the
-            # peers' staging vectors (after a barrier, or once their flags say so)
+        if direct:
+            # every pair of rank slots is computed once, in ONE launch: own block + the anchors of the ranks ahead
+            # on the ring against the local keys; the partial row sums of those anchors are added straight into
+            # their owners' row sums over NVLink, and the kernel's last CTA waits for the peers' signals and runs
+            # the per-row tail (maai_ntxent_fwd_sym_direct)
+            with _Profiler.span("fwd"):
+                _lib.check(lib.maai_ntxent_fwd_sym_direct(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(pos_cos),
+                                                          _ptr(rowsum), ws.w_host[i], _ptr(r_row),
+                                                          _ptr(ws.r_tab[i]) if peer_r else None,
+                                                          ws.mc_r[i] if peer_r else None, _ptr(loss), psync, st),
+                           "maai_ntxent_fwd_sym_direct")
+        elif _sym_forward_enabled(b, dp, world):
+            # staged form: the other half of each row sum arrives through the peers' staging vectors (after a
+            # barrier, or once their flags say so) and a separate finalize kernel pulls them
             with _Profiler.span("fwd"):
                 _lib.check(lib.maai_ntxent_fwd_sym_tiles(_ptr(z_all), b, world, rank, dp, inv_tau, _ptr(rowsum),
                                                          _ptr(ws.stage[i]), _lib.F_PREZEROED, psync, st),

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # MAAI_DEBUG_LIB selects an A/B build of the same library (tools/ab_variants.py); never a fallback
 LIB_PATH = os.environ.get("MAAI_DEBUG_LIB") or os.path.join(HERE, "libmaai_ntxent.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 F_PREZEROED = 1
 WS_CTL_WORDS = 32
 OK, E_ARG, E_SHAPE, E_CUDA = 0, -1, -2, -3
@@ -56,6 +56,8 @@ SIGNATURES = {
                                            _c_int, _c_sync_p, _c_void_p]),
     "maai_ntxent_fwd_sym_finalize": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p,
                                               _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_sync_p, _c_void_p]),
+    "maai_ntxent_fwd_sym_direct": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p,
+                                            _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_sync_p, _c_void_p]),
     "maai_ntxent_bwd_tiles": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float,
                                        _c_int, _c_void_p, _c_void_p]),
     "maai_ntxent_bwd_keyside": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_float,

@@ -527,7 +527,8 @@ static GroupPlan plan_groups(int b, int world, int rank, int rb_rows, int nq) {
 
 template <int D, int NQ>
 static int launch_tile_groups(const void* z_glob, int b, int world, int rank, float inv_tau, float* rowsum_l,
-                              float* stage, cudaStream_t s, const maai_peer_sync* sync) {
+                              float* stage, cudaStream_t s, const maai_peer_sync* sync,
+                              const void* const* peer_rowsum_host = nullptr, const maai::FinalizeArgs* fin = nullptr) {
   using C = maai::TileCfg<D, false, NQ>;
   static std::atomic<unsigned long long> attr_done{0};
   cudaError_t attr_err =
@@ -557,8 +558,20 @@ static int launch_tile_groups(const void* z_glob, int b, int world, int rank, fl
     p.g_rows[g] = gp.rows[g];
     p.g_nkt[g] = gp.nkt[g];
     p.g_items[g] = gp.items[g];
-    // group 0: this rank's own row sums; others: slot of the anchors' owner in the staging vectors
-    p.g_out[g] = g == 0 ? rowsum_l : stage + gp.qrow0[g];  // stage is (world, 2b): indexed by global row
+    // group 0: this rank's own row sums; others: the anchors' owner -- its slot of this rank's staging vectors
+    // ((world, 2b), indexed by global row), or, in direct mode, the owner's own row sums over NVLink
+    if (g == 0) {
+      p.g_out[g] = rowsum_l;
+    } else if (peer_rowsum_host) {
+      const int q = gp.qrow0[g] / m_loc;
+      p.g_out[g] = static_cast<float*>(const_cast<void*>(peer_rowsum_host[q])) + (gp.qrow0[g] - q * m_loc);
+    } else {
+      p.g_out[g] = stage + gp.qrow0[g];
+    }
+  }
+  if (fin) {  // direct mode: the per-row tail runs in this kernel (TileParams::done_ctr doubles as the marker)
+    p.done_ctr = reinterpret_cast<unsigned int*>(rowsum_l + m_loc);
+    p.fin = *fin;
   }
   p.ngroups = gp.ng;
   p.total_items = gp.total;
@@ -671,6 +684,30 @@ int maai_ntxent_fwd_sym_tiles(const void* z_glob, int b, int world, int rank, in
     case 64: return launch_tile_groups<64, 2>(z_glob, b, world, rank, inv_tau, rowsum_l, stage, s, sync);
     case 128: return launch_tile_groups<128, 2>(z_glob, b, world, rank, inv_tau, rowsum_l, stage, s, sync);
     case 256: return launch_tile_groups<256, 1>(z_glob, b, world, rank, inv_tau, rowsum_l, stage, s, sync);
+    default: return fail(MAAI_E_SHAPE, "d_pad must be 64, 128 or 256");
+  }
+}
+
+int maai_ntxent_fwd_sym_direct(const void* z_glob, int b, int world, int rank, int d_pad, float inv_tau,
+                               const float* pos_cos, float* rowsum_l, const void* const* peer_rowsum_host,
+                               float* r_out, const void* const* peer_r_bases, void* mc_r_base, float* loss_out,
+                               const maai_peer_sync* sync, void* stream) {
+  if (!z_glob || !pos_cos || !rowsum_l || !peer_rowsum_host || !loss_out || !sync) return fail(MAAI_E_ARG, "null pointer");
+  int rc = check_common(b, world, rank);
+  if (rc != MAAI_OK) return rc;
+  if (world > 2 * (maai::kMaxGroups - 1)) return fail(MAAI_E_SHAPE, "symmetric forward: world must be <= 16");
+  if (!(inv_tau > 0.f)) return fail(MAAI_E_ARG, "temperature must be positive");
+  if (!aligned16(z_glob)) return fail(MAAI_E_ARG, "z_glob must be 16-byte aligned");
+  if (check_sync(sync, world) != MAAI_OK) return MAAI_E_ARG;
+  for (int q = 0; q < world; ++q)
+    if (!peer_rowsum_host[q]) return fail(MAAI_E_ARG, "peer_rowsum_host: null entry");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const maai::FinalizeArgs fin =
+      make_fin(rowsum_l, pos_cos, b, inv_tau, r_out, loss_out, peer_r_bases, world, rank, mc_r_base, nullptr, sync);
+  switch (d_pad) {
+    case 64: return launch_tile_groups<64, 2>(z_glob, b, world, rank, inv_tau, rowsum_l, nullptr, s, sync, peer_rowsum_host, &fin);
+    case 128: return launch_tile_groups<128, 2>(z_glob, b, world, rank, inv_tau, rowsum_l, nullptr, s, sync, peer_rowsum_host, &fin);
+    case 256: return launch_tile_groups<256, 1>(z_glob, b, world, rank, inv_tau, rowsum_l, nullptr, s, sync, peer_rowsum_host, &fin);
     default: return fail(MAAI_E_SHAPE, "d_pad must be 64, 128 or 256");
   }
 }

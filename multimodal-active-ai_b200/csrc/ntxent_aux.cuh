@@ -57,9 +57,10 @@ __device__ __forceinline__ void signal_peers(const PeerSync& s, int kind) {
     st_release_sys_u32(reinterpret_cast<unsigned int*>(s.peer_flags[threadIdx.x]) + kind * kFlagStride + s.rank, s.seq);
 }
 // Tail of a multi-CTA producer kernel: every thread has issued its peer stores; the last CTA to get here
-// signals.  Must be reached by all threads of all CTAs (no early return before it).
-__device__ __forceinline__ void signal_when_grid_done(const PeerSync& s, int kind) {
-  if (!s.peer_flags) return;
+// signals.  Must be reached by all threads of all CTAs (no early return before it).  Returns true in every
+// thread of that last CTA (false everywhere when signalling is off).
+__device__ __forceinline__ bool signal_when_grid_done(const PeerSync& s, int kind) {
+  if (!s.peer_flags) return false;
   __shared__ unsigned int is_last;
   __syncthreads();  // every thread of the CTA has issued its peer / multicast stores ...
   if (threadIdx.x == 0) {
@@ -73,6 +74,7 @@ __device__ __forceinline__ void signal_when_grid_done(const PeerSync& s, int kin
     signal_peers(s, kind);
     if (threadIdx.x == 0) *s.counter = 0u;  // ready for the next launch
   }
+  return is_last != 0u;
 }
 
 constexpr float kNormEps = 1e-12f;  // F.normalize default eps (Objective.py:42-43)

@@ -411,27 +411,37 @@ struct GrpWalk {
   }
 };
 
-// Forward, last CTA done: every other CTA's sums are in L2 (their threads fenced before the CTA took its
-// ticket), so this CTA runs the per-row tail (finalize_rows) over all 2b rows.  Out of line on purpose: it
-// runs once per launch and must not cost the hot loops a register.  flag_smem / part_smem: shared-window
-// addresses of dead regions (the mbarriers, the Q tiles).
+// Per-row tail of the forward inside the tile kernel, run by ONE CTA once every CTA's sums are complete
+// (finalize_rows over all 2b rows, fixed-order fp64 sum, loss, row factors + their peer stores + the FLAG_R
+// signal).  Out of line on purpose: it runs once per launch and must not cost the hot loops a register.
+// part_smem: shared-window address of a dead region (the Q tiles).  wait_l: cross-rank symmetric forward in
+// "direct" mode -- the peers add their partial row sums straight into this rank's row sums (NVLink
+// red.add); they are complete once every peer has signalled FLAG_L.
+__device__ __noinline__ void tail_finalize_body(const TileParams& p, uint32_t part_smem, bool wait_l) {
+  if (wait_l) {
+    if (threadIdx.x < 32)
+      wait_all_peers(p.grp_sync.local_flags, FLAG_L, p.grp_sync.seq, p.grp_sync.world, p.grp_sync.rank, p.grp_sync.timeout_s);
+    __syncthreads();
+  }
+  __threadfence();
+  double* part = static_cast<double*>(__cvta_shared_to_generic(part_smem));
+  const double acc = finalize_rows(p.fin, threadIdx.x, blockDim.x);
+  if (p.fin.sync.peer_flags) __threadfence_system();  // this thread's row-factor stores to the peers
+  const double v = finalize_block_sum(acc, part);     // (contains a CTA barrier)
+  if (threadIdx.x == 0) *p.fin.loss_out = float(v / double(p.fin.b));
+  if (p.fin.sync.peer_flags) {
+    __syncthreads();
+    __threadfence_system();
+    signal_peers(p.fin.sync, FLAG_R);
+  }
+}
+// Forward, single launch: the last CTA to finish (ticket on done_ctr; every other CTA's threads fenced their
+// sums before their CTA took its ticket) runs the tail.  flag_smem: a dead shared word (the mbarriers).
 __device__ __noinline__ void fwd_tail_finalize(const TileParams& p, uint32_t flag_smem, uint32_t part_smem) {
   uint32_t* flag = static_cast<uint32_t*>(__cvta_shared_to_generic(flag_smem));
   if (threadIdx.x == 0) *flag = (atomicAdd(p.done_ctr, 1u) == gridDim.x - 1) ? 1u : 0u;
   __syncthreads();
-  if (*flag) {
-    __threadfence();
-    double* part = static_cast<double*>(__cvta_shared_to_generic(part_smem));
-    const double acc = finalize_rows(p.fin, threadIdx.x, blockDim.x);
-    if (p.fin.sync.peer_flags) __threadfence_system();  // this thread's row-factor stores to the peers
-    const double v = finalize_block_sum(acc, part);     // (contains a CTA barrier)
-    if (threadIdx.x == 0) *p.fin.loss_out = float(v / double(p.fin.b));
-    if (p.fin.sync.peer_flags) {
-      __syncthreads();
-      __threadfence_system();
-      signal_peers(p.fin.sync, FLAG_R);
-    }
-  }
+  if (*flag) tail_finalize_body(p, part_smem, false);
 }
 
 template <int D, bool BWD, int NQ, bool RANK = false, bool SYM = false, bool GRP = false>
@@ -1097,8 +1107,13 @@ ntxent_tile_kernel(const __grid_constant__ CUtensorMap tmap_q,
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
   if (!BWD && !GRP && p.done_ctr) fwd_tail_finalize(p, smem_base + C::OFF_BAR, smem_base + C::OFF_Q);
-  // cross-rank symmetric forward: the staged partial sums for the peers are complete once every CTA is here
-  if (GRP) signal_when_grid_done(p.grp_sync, FLAG_L);
+  // cross-rank symmetric forward: this rank's partial sums for the peers (staged here, or added straight into
+  // the owners' row sums) are complete once every CTA is here; in direct mode (done_ctr set) the CTA that
+  // signalled then waits for the peers' signals and runs the per-row tail itself
+  if (GRP) {
+    const bool last = signal_when_grid_done(p.grp_sync, FLAG_L);
+    if (last && p.done_ctr) tail_finalize_body(p, smem_base + C::OFF_Q, true);
+  }
 }
 
 }  // namespace maai

@@ -311,3 +311,12 @@ def test_emulated_ranks_inkernel_flags(world, b, d, tau, sym):
             torch.cuda.synchronize()
             assert rel_fro(g1.cpu().numpy(), o1[p]) <= 1e-2, (seq, p)
             assert rel_fro(g2.cpu().numpy(), o2[p]) <= 1e-2, (seq, p)
+
+
+def test_emulated_ranks_direct_symmetric_forward():
+    """maai_ntxent_fwd_sym_direct (cross-rank symmetric forward in one launch: remote red.add of the partial row
+    sums, kind-2 flags, per-row tail in the kernel): emulated ranks on concurrent streams, in a subprocess
+    (tests/_emulated_direct_worker.py explains why), losses and full gradients against the fp64 oracle."""
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_emulated_direct_worker.py")],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "EMU_DIRECT_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
