@@ -266,7 +266,8 @@ def main():
             return dict(gather_mode="nccl all_gather_into_tensor", sym_forward=False)
         ws = P.PeerWorkspace.get(bb, dp, world, rank, dev, None)
         return dict(gather_mode="peer stores, NVSwitch multicast" if ws.mc_z[0] else "peer stores, unicast",
-                    sym_forward=bool(P._sym_forward_enabled(bb, dp, world)))
+                    sym_forward=P._sym_forward_mode(bb, dp, world, ws.use_flags) != "off",
+                    sym_forward_mode=P._sym_forward_mode(bb, dp, world, ws.use_flags), peer_order="in-kernel flags" if ws.use_flags else "barrier launches")
 
     def make_inputs(bb, r=None):
         g = torch.Generator(device=dev).manual_seed(1234 + (rank if r is None else r))
@@ -462,8 +463,9 @@ def main():
     h_in = torch.empty(2, b, d).pin_memory()
     h_in[0].copy_(torch.randn(b, d, generator=g))
     h_in[1].copy_(torch.randn(b, d, generator=g))
-    h_out = [torch.empty(2 * n_in + 1).pin_memory() for _ in range(2)]
-    d_in = [torch.empty(2, b, d, device=dev) for _ in range(2)]
+    NSLOT = 4  # depth of the host<->device pipeline (the host consumes slot i's results before reusing it at i+NSLOT)
+    h_out = [torch.empty(2 * n_in + 1).pin_memory() for _ in range(NSLOT)]
+    d_in = [torch.empty(2, b, d, device=dev) for _ in range(NSLOT)]
 
     def e2e_serial_step():
         d_in[0].copy_(h_in, non_blocking=True)
@@ -480,26 +482,26 @@ def main():
     in_s = torch.cuda.Stream(device=dev)
     out_s = torch.cuda.Stream(device=dev)
     main_s = torch.cuda.current_stream()
-    ev_in = [torch.cuda.Event() for _ in range(2)]      # inputs of the slot are on the device
-    ev_done = [torch.cuda.Event() for _ in range(2)]    # results of the slot are computed
-    ev_out = [torch.cuda.Event() for _ in range(2)]     # results of the slot are on the host
+    ev_in = [torch.cuda.Event() for _ in range(NSLOT)]      # inputs of the slot are on the device
+    ev_done = [torch.cuda.Event() for _ in range(NSLOT)]    # results of the slot are computed
+    ev_out = [torch.cuda.Event() for _ in range(NSLOT)]     # results of the slot are on the host
 
     e2e_host = {}
 
     def e2e_pipelined(steps):
-        keep = [None, None]  # the slot's device results stay referenced until their D2H copy has been consumed
+        keep = [None] * NSLOT  # the slot's device results stay referenced until their D2H copy has been consumed
         e2e_host["t0"] = time.perf_counter()
 
         def h2d(i):
-            s_ = i & 1
+            s_ = i % NSLOT
             with torch.cuda.stream(in_s):
-                if i >= 2:
+                if i >= NSLOT:
                     in_s.wait_event(ev_done[s_])  # the step that read this slot's inputs has finished
                 d_in[s_].copy_(h_in, non_blocking=True)
                 ev_in[s_].record(in_s)
         h2d(0)
         for i in range(steps):
-            s_ = i & 1
+            s_ = i % NSLOT
             if i + 1 < steps:
                 h2d(i + 1)  # prefetch the next step's inputs while this step computes
             main_s.wait_event(ev_in[s_])
@@ -509,7 +511,7 @@ def main():
                                                     device=dev, key_grad=True)
             loss.backward()
             ev_done[s_].record(main_s)
-            if i >= 2:
+            if i >= NSLOT:
                 ev_out[s_].synchronize()  # the host has consumed this slot's previous results
             keep[s_] = (loss, x, y)
             with torch.cuda.stream(out_s):
@@ -519,7 +521,7 @@ def main():
                 h_out[s_][2 * n_in:].copy_(loss.detach().view(1), non_blocking=True)
                 ev_out[s_].record(out_s)
         e2e_host["issue_s"] = time.perf_counter() - e2e_host["t0"]
-        for s_ in range(min(2, steps)):
+        for s_ in range(min(NSLOT, steps)):
             ev_out[s_].synchronize()
 
     def timed_e2e(fn_steps):
@@ -538,7 +540,7 @@ def main():
         """the H2D + D2H traffic of the e2e schedule without any compute: the PCIe / host-memory floor of e2e"""
         dummy = torch.empty(2 * n_in + 1, device=dev)
         for i in range(steps):
-            s_ = i & 1
+            s_ = i % NSLOT
             with torch.cuda.stream(in_s):
                 d_in[s_].copy_(h_in, non_blocking=True)
             with torch.cuda.stream(out_s):
@@ -553,7 +555,7 @@ def main():
     copy_floor_s = timed_e2e(copies_only)
     e2e_serial_s = timed_e2e(lambda k: [e2e_serial_step() for _ in range(k)])
     e2e_pipe_s = timed_e2e(e2e_pipelined)
-    e2e_loss = float(h_out[(args.steps - 1) & 1][2 * n_in])
+    e2e_loss = float(h_out[(args.steps - 1) % NSLOT][2 * n_in])
     e2e_s = min(e2e_pipe_s, e2e_serial_s)
     e2e_mode = "pipelined" if e2e_pipe_s <= e2e_serial_s else "serial"
     e2e_pairs = B * args.steps / e2e_s
@@ -679,7 +681,7 @@ def main():
                     "what": "every step: ONE pinned host buffer [h1|h2] -> device, contrastive_loss + backward, "
                             "[dh1|dh2|loss] -> ONE pinned host buffer; wall clock over all steps, max over ranks.  Two "
                             "schedules are timed and value is the faster one (schedule): pipelined = H2D and D2H on their "
-                            "own streams, double-buffered (H2D of step i+1 / D2H of step i-1 overlap the kernels of step "
+                            "own streams, four slots deep (H2D of step i+1 / D2H of step i-1 overlap the kernels of step "
                             "i); serial = one stream, host sync after every step"},
             "gpu_launches": int(main_r["launches"]),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",

@@ -274,18 +274,27 @@ class PeerWorkspace:
 _peer_state = {"ok": None}
 
 
-def _sym_forward_enabled(b, dp, world) -> bool:
-    """Cross-rank symmetric forward (peer mode only).  A tile that serves a row AND a column costs 1.29x
-    a plain one, the split adds a barrier and a second small kernel (~30 us): measured at 32768 pairs,
-    d=128 it wins at 2 ranks (forward 0.54 -> 0.43 ms, step 1.44 -> 1.30 ms), is marginal at 4 (step 0.732
-    -> 0.718 ms) and a wash at 8 (0.145 vs 0.155 ms), so it is used from 16384 rows per rank up.
-    MAAI_FWD_SYM_MULTI=1 / 0 force it on / off; at most 16 ranks (group table of the kernel)."""
+def _sym_forward_mode(b, dp, world, flags: bool) -> str:
+    """Cross-rank symmetric forward (peer mode only): "off", "staged" (partial row sums staged locally, pulled by
+    a finalize kernel: maai_ntxent_fwd_sym_tiles + _finalize) or "direct" (added straight into the owners' row
+    sums over NVLink, per-row tail inside the one launch: maai_ntxent_fwd_sym_direct; needs the in-kernel flags).
+    A tile that serves a row AND a column costs 1.5x a plain one, so halving the tile count buys 25 % of the tile
+    time, against which stand the exchange of the partial sums and a per-row tail that waits for the peers.
+    Measured at 32768 pairs, d=128 (profiles/r2_tuning_log.md): 2 ranks x 16384 pairs staged 1.273 ms/step, direct
+    1.288, off 1.36 -> staged from 16384 rows per rank up; 8 ranks x 4096 pairs: see the tuning log.
+    MAAI_FWD_SYM_MULTI = 0 / staged / direct forces a mode (1 = staged); at most 16 ranks (group table)."""
     v = os.environ.get("MAAI_FWD_SYM_MULTI", "")
     if v == "0" or world > 16:
-        return False
-    if v == "1":
-        return True
-    return 2 * b >= 16384
+        return "off"
+    if v == "direct":
+        return "direct" if flags else "staged"
+    if v in ("1", "staged"):
+        return "staged"
+    return "staged" if 2 * b >= 16384 else "off"
+
+
+def _sym_forward_enabled(b, dp, world) -> bool:
+    return _sym_forward_mode(b, dp, world, True) != "off"
 
 
 def peer_gather_available() -> bool:
@@ -426,7 +435,8 @@ class _NTXentFunction(torch.autograd.Function):
         sync = ws.sync_for(ws.seq)   # ctypes struct (kept alive until the calls below have returned) or None
         psync = ctypes.byref(sync) if sync is not None else None
         z_all = ws.z[i]
-        direct = sync is not None and _sym_forward_enabled(b, dp, world) and os.environ.get("MAAI_SYM_DIRECT", "1") != "0"
+        sym_mode = _sym_forward_mode(b, dp, world, sync is not None)
+        direct = sym_mode == "direct"
         if direct:  # the peers add into this rank's row sums: the step workspace lives in the symmetric allocation
             wsp = ws.wsbuf[i]
             rowsum = wsp[:2 * b]
@@ -472,7 +482,7 @@ class _NTXentFunction(torch.autograd.Function):
                                                           _ptr(ws.r_tab[i]) if peer_r else None,
                                                           ws.mc_r[i] if peer_r else None, _ptr(loss), psync, st),
                            "maai_ntxent_fwd_sym_direct")
-        elif _sym_forward_enabled(b, dp, world):
+        elif sym_mode == "staged":
             # staged form: the other half of each row sum arrives through the peers' staging vectors (after a
             # barrier, or once their flags say so) and a separate finalize kernel pulls them
             with _Profiler.span("fwd"):

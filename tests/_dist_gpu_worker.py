@@ -22,9 +22,11 @@ def main():
     ok = True
     from maai_b200.Objective import peer_gather_available
     # (peer gather?, cross-rank symmetric forward forced on / off)
-    modes = [(False, "0")] + ([(True, "0"), (True, "1")] if peer_gather_available() else [])
+    modes = [(False, "0")] + ([(True, "0"), (True, "1"), (True, "direct")] if peer_gather_available() else [])
     if rank == 0:
-        print("modes under test (peer: False = NCCL all_gather, True = fused NVLink peer stores; sym forward):", modes)
+        print("modes under test (peer: False = NCCL all_gather, True = fused NVLink peer stores; cross-rank symmetric "
+              "forward: 0 = off, 1 = staged, direct = one launch with remote adds):", modes,
+              "| ordering of the peer stores:", "barrier launches" if os.environ.get("MAAI_PEER_FLAGS") == "0" else "in-kernel flags")
     for (b, d, tau), (peer, sym) in [(c, m) for c in ((192, 128, 0.5), (1000, 64, 0.1), (512, 256, 0.2)) for m in modes]:
         os.environ["MAAI_FWD_SYM_MULTI"] = sym
         g = torch.Generator().manual_seed(77)
