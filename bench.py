@@ -343,6 +343,28 @@ def main():
         raise SystemExit("--require-peer: the fused peer-store gathers are not the mode that ran: "
                          + json.dumps(path_used(b)))
 
+    def warm_up(fn, warmup):
+        """W untimed steps as asked, then more of them until the GPU has been busy for ~20 ms: after the parity
+        gate's CPU work the SM clock sits at idle (120 MHz) and W = 3..5 steps of 0.4 ms (8 GPUs) end before it
+        has ramped up -- the first timed steps then run slow (step maxima 0.57 vs 0.40 ms median).  Not longer:
+        0.15 s of warm-up already spends the box's power budget and the "short" run then measures the capped
+        clock (2 GPUs: 1.28 -> 1.42 ms at 1680 MHz, sw_power_cap) -- that regime is what the 200-step run
+        reports.  Every rank runs the same number of steps (rank 0 decides): they depend on each other."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        per = max(1e-5, (time.perf_counter() - t0) / warmup)
+        n = torch.tensor([max(0, min(500, int(0.02 / per)))], device=dev, dtype=torch.int64)
+        if world > 1:
+            dist.broadcast(n, 0)
+        for _ in range(int(n)):
+            fn()
+        barrier()
+
     def timed_run(bb, steps, warmup, profile, grad1=True, sample_clocks=False):
         h1, h2 = make_inputs(bb)
         x = h1.requires_grad_(grad1)
@@ -350,9 +372,7 @@ def main():
         sampler = ClockSampler(local_rank) if (sample_clocks and rank == 0) else None
         if sampler:
             sampler.start()  # a separate process: its start-up overlaps the warm-up steps
-        for _ in range(warmup):
-            step(x, y)
-        barrier()
+        warm_up(lambda: step(x, y), warmup)
         _Profiler.reset()
         _Profiler.enabled = profile
         if sampler:
@@ -423,9 +443,7 @@ def main():
             loss = fn(x, y)
             loss.backward()
             return loss
-        for _ in range(warmup):
-            gstep()
-        torch.cuda.synchronize()
+        warm_up(gstep, warmup)
         evs = []
         for _ in range(steps):
             flush_buf.fill_(1)
@@ -441,15 +459,14 @@ def main():
 
     # ---------------- main timed region (device-resident inputs) ----------------
     # Two run lengths, the short one first: short runs see boost clocks (~1.9 GHz), 200 back-to-back steps run
-    # into the power cap (MEASURED_PEAKS: burst vs sustained).  The line's value is the one --steps names;
-    # both are reported with their clocks.
+    # into the power cap (MEASURED_PEAKS: burst vs sustained).  The line's value is the one --steps names; both
+    # are reported with their clocks.  e2e is measured right after the run --steps names, i.e. in the same
+    # clock regime as `value` (the other run length follows the e2e block when it is the long one).
     other_steps = 20 if args.steps >= 100 else 200
+    other_r = None
     if args.steps >= 100:
         other_r = timed_run(b, other_steps, args.warmup, profile=False, sample_clocks=True)
-        main_r = timed_run(b, args.steps, args.warmup, profile=True, sample_clocks=True)
-    else:
-        main_r = timed_run(b, args.steps, args.warmup, profile=True, sample_clocks=True)
-        other_r = timed_run(b, other_steps, args.warmup, profile=False, sample_clocks=True)
+    main_r = timed_run(b, args.steps, args.warmup, profile=True, sample_clocks=True)
     clocks = main_r["clocks"]
 
     # ---------------- end to end through the public API with HOST buffers ----------------
@@ -491,6 +508,7 @@ def main():
     def e2e_pipelined(steps):
         keep = [None] * NSLOT  # the slot's device results stay referenced until their D2H copy has been consumed
         e2e_host["t0"] = time.perf_counter()
+        e2e_host["spans"] = []
 
         def h2d(i):
             s_ = i % NSLOT
@@ -507,9 +525,14 @@ def main():
             main_s.wait_event(ev_in[s_])
             x = d_in[s_][0].detach().requires_grad_(True)
             y = d_in[s_][1].detach().requires_grad_(True)
+            c0 = torch.cuda.Event(enable_timing=True)
+            c1 = torch.cuda.Event(enable_timing=True)
+            c0.record(main_s)
             loss, _, _ = maai_b200.contrastive_loss(x, y, temperature=tau, local_rank=rank, world_size=world,
                                                     device=dev, key_grad=True)
             loss.backward()
+            c1.record(main_s)
+            e2e_host.setdefault("spans", []).append((c0, c1))
             ev_done[s_].record(main_s)
             if i >= NSLOT:
                 ev_out[s_].synchronize()  # the host has consumed this slot's previous results
@@ -548,19 +571,23 @@ def main():
         in_s.synchronize()
         out_s.synchronize()
 
+    e2e_pipelined(args.warmup)
+    e2e_pipe_s = timed_e2e(e2e_pipelined)  # first: same clock regime as the device-resident run just before
+    e2e_compute_ms = statistics.mean(a.elapsed_time(e) for a, e in e2e_host["spans"]) if e2e_host.get("spans") else None
     for _ in range(args.warmup):
         e2e_serial_step()
-    e2e_pipelined(args.warmup)
     copies_only(args.warmup)
     copy_floor_s = timed_e2e(copies_only)
     e2e_serial_s = timed_e2e(lambda k: [e2e_serial_step() for _ in range(k)])
-    e2e_pipe_s = timed_e2e(e2e_pipelined)
     e2e_loss = float(h_out[(args.steps - 1) % NSLOT][2 * n_in])
     e2e_s = min(e2e_pipe_s, e2e_serial_s)
     e2e_mode = "pipelined" if e2e_pipe_s <= e2e_serial_s else "serial"
     e2e_pairs = B * args.steps / e2e_s
     h2d_bytes = 2 * b * d * 4
     d2h = 2 * b * d * 4 + 4
+
+    if other_r is None:
+        other_r = timed_run(b, other_steps, args.warmup, profile=False, sample_clocks=True)
 
     # ---------------- secondary: configs[1] (4096 pairs, 1 GPU) ----------------
     secondary = None
@@ -673,6 +700,7 @@ def main():
                     "schedule": e2e_mode, "loss_read_on_host": e2e_loss,
                     "pipelined_ms_per_step": e2e_pipe_s / args.steps * 1e3,
                     "pipelined_host_issue_ms_per_step": e2e_host.get("issue_s", 0.0) / args.steps * 1e3,
+                    "pipelined_compute_span_ms": e2e_compute_ms,
                     "copies_only_ms_per_step": copy_floor_s / args.steps * 1e3,
                     "copies_only_note": "the same H2D + D2H bytes per step on the two copy streams with NO compute, all ranks "
                                         "at once: the PCIe / host-memory floor of e2e on this box (e2e >= max(this, ms_per_step))",
