@@ -344,12 +344,13 @@ def main():
                          + json.dumps(path_used(b)))
 
     def warm_up(fn, warmup):
-        """W untimed steps as asked, then more of them until the GPU has been busy for ~20 ms: after the parity
+        """2 W untimed steps, then more of them until the GPU has been busy for ~10 ms in total: after the parity
         gate's CPU work the SM clock sits at idle (120 MHz) and W = 3..5 steps of 0.4 ms (8 GPUs) end before it
         has ramped up -- the first timed steps then run slow (step maxima 0.57 vs 0.40 ms median).  Not longer:
-        0.15 s of warm-up already spends the box's power budget and the "short" run then measures the capped
-        clock (2 GPUs: 1.28 -> 1.42 ms at 1680 MHz, sw_power_cap) -- that regime is what the 200-step run
-        reports.  Every rank runs the same number of steps (rank 0 decides): they depend on each other."""
+        warm-up spends the box's power budget and the "short" run then measures the capped clock (2 GPUs after
+        0.15 s of warm-up: 1.28 -> 1.42 ms at 1680 MHz, sw_power_cap; 1 GPU after 35 ms: 2.35 -> 2.47 ms) --
+        that regime is what the 200-step run reports.  At 1 GPU (2.3 ms per step) nothing is added.  Every rank
+        runs the same number of steps (rank 0 decides): they depend on each other."""
         for _ in range(warmup):
             fn()
         barrier()
@@ -358,7 +359,7 @@ def main():
             fn()
         torch.cuda.synchronize()
         per = max(1e-5, (time.perf_counter() - t0) / warmup)
-        n = torch.tensor([max(0, min(500, int(0.02 / per)))], device=dev, dtype=torch.int64)
+        n = torch.tensor([max(0, min(500, int(0.010 / per) - 2 * warmup))], device=dev, dtype=torch.int64)
         if world > 1:
             dist.broadcast(n, 0)
         for _ in range(int(n)):
