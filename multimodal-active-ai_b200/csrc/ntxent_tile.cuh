@@ -101,6 +101,13 @@
 #ifndef MAAI_NQ1_TEAMS
 #define MAAI_NQ1_TEAMS 2
 #endif
+// Backward softmax: exponentials and the P = E (r_i + r_j) -> bf16 post-processing in source-level software
+// pipeline over groups of this many column pairs (0 = all exponentials of a chunk first, then all the
+// post-processing: ptxas then issues the chunk's 32 MUFU.EX2 as one burst, and 39.7 % of the backward's warp
+// samples sit in mio_throttle on them, profiles/r2_ncu_summary_v1.md).
+#ifndef MAAI_BWD_ILV
+#define MAAI_BWD_ILV 0
+#endif
 
 // Per-warp phase timers (clock64) for tools/phase_prof.py; compiled out unless MAAI_PROF=1.
 #ifndef MAAI_PROF
@@ -293,6 +300,45 @@ __device__ __forceinline__ void softmax_chunk(uint32_t (&v)[CW], uint32_t (&pk)[
   // packed f32x2 math throughout (FFMA2 / FADD2 / FMUL2): half the FMA-pipe issue slots
   const float2 c1p = make_float2(cx.c1, cx.c1), c1n = make_float2(-cx.c1, -cx.c1);
   constexpr int NP = CW / 2;  // column pairs
+  if (BWD && MAAI_BWD_ILV > 0 && POLY == 0 && !(MAAI_ABL & 1)) {
+    // software pipeline: exponentials of group g + 1 are issued before the post-processing of group g
+    constexpr int G = MAAI_BWD_ILV > 0 ? MAAI_BWD_ILV : 2, NG = NP / G;
+    static_assert(NP % G == 0 && G % 2 == 0, "group size");
+    const float2 ri2 = make_float2(cx.r_i, cx.r_i);
+    float2 ec[G], en[G];
+    auto expo = [&](int g, float2 (&o)[G]) {
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const int jj = g * G + j;
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[2 * jj]), __uint_as_float(v[2 * jj + 1])), c1p, c1n);
+        o[j].x = ex2_approx_v(x.x);
+        o[j].y = ex2_approx_v(x.y);
+        if (special) {
+          const int kc = kc0 + 2 * jj;
+          if (kc == cx.grow || kc == cx.gpos || kc >= cx.m_glob) o[j].x = 0.f;
+          if (kc + 1 == cx.grow || kc + 1 == cx.gpos || kc + 1 >= cx.m_glob) o[j].y = 0.f;
+        }
+      }
+    };
+    expo(0, ec);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      if (g + 1 < NG) expo(g + 1, en);
+#pragma unroll
+      for (int j = 0; j < G; j += 2) {
+        const int jj = g * G + j;
+        const float4 rj = *reinterpret_cast<const float4*>(rk + 2 * jj);
+        const float2 p0 = __fmul2_rn(ec[j], __fadd2_rn(ri2, make_float2(rj.x, rj.y)));
+        const float2 p1 = __fmul2_rn(ec[j + 1], __fadd2_rn(ri2, make_float2(rj.z, rj.w)));
+        pk[jj] = pack_bf16x2_v(p0.x, p0.y);
+        pk[jj + 1] = pack_bf16x2_v(p1.x, p1.y);
+      }
+#pragma unroll
+      for (int j = 0; j < G; ++j) ec[j] = en[j];
+    }
+    CX_MARK(2);
+    return;
+  }
   float2 e[NP];
 #pragma unroll
   for (int j = 0; j < NP; ++j) {

@@ -354,6 +354,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// volatile twins: the compiler keeps volatile asm statements in source order relative to each other, which is
+// how the backward's software pipeline (MAAI_BWD_ILV) keeps its exponentials and packs interleaved
+__device__ __forceinline__ float ex2_approx_v(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_v(float lo, float hi) {
+  uint32_t r;
+  asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 // 2^(s*c) for a pair of dot products on the FMA/ALU pipes (no MUFU), |s*c| <= 126.
 // One FFMA2 forms t = s*c + 1.5*2^23, which rounds y = s*c to the nearest integer n in the low
 // mantissa bits; f = y - n in [-0.5, 0.5] comes from a second FFMA2 (single rounding of s*c - n);
