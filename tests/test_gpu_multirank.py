@@ -320,3 +320,25 @@ def test_emulated_ranks_direct_symmetric_forward():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_emulated_direct_worker.py")],
                          capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "EMU_DIRECT_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-3000:]
+
+
+def test_tensors_on_a_non_current_device():
+    """one process, two GPUs -- the tensors live on cuda:1 while cuda:0 is the current device.  The host
+    mirror makes the tensors' device current for the C-ABI calls (and takes ITS stream), the library keeps its
+    per-device caches (SM count, dynamic shared-memory attribute) by device ordinal."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import maai_b200
+    from oracle import ntxent_oracle as O
+    torch.cuda.set_device(0)
+    g = torch.Generator().manual_seed(3)
+    h1 = torch.randn(300, 128, generator=g); h2 = h1 + 0.5 * torch.randn(300, 128, generator=g)
+    ol, o1, o2 = O.contrastive_loss_oracle(h1.numpy(), h2.numpy(), 0.5)
+    for dev in ("cuda:1", "cuda:0", "cuda:1"):
+        x = h1.to(dev).requires_grad_(True); y = h2.to(dev).requires_grad_(True)
+        loss = maai_b200.contrastive_loss(x, y, temperature=0.5)[0]
+        loss.backward()
+        torch.cuda.synchronize(dev)
+        assert torch.cuda.current_device() == 0
+        assert abs(float(loss.detach()) - ol) <= 1e-3 * abs(ol), dev
+        assert rel_fro(x.grad.cpu().numpy(), o1) <= 1e-2 and rel_fro(y.grad.cpu().numpy(), o2) <= 1e-2, dev
