@@ -65,7 +65,11 @@ def main():
     views = [(base + 0.2 * torch.randn(b, 3, a.image, a.image, generator=g, device=dev)).contiguous(memory_format=torch.channels_last)
              for _ in range(8)]   # a small pool of augmentations of the same images, cycled
     curves = {}
-    for arm in ("reference", "fused"):
+    # Two more arms put the fused arm's deviation in proportion: the reference a second time (is the reference itself
+    # reproducible here?) and the reference fed with embeddings rounded to bf16 (straight-through gradient) -- a
+    # perturbation of the size of the bf16 tensor-core operands of the fused path; training through the plateau and
+    # the sharp drop of this loss curve amplifies any such perturbation.
+    for arm in ("reference", "fused", "reference_again", "reference_bf16_inputs"):
         model = copy.deepcopy(proto)
         if world > 1:
             model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank])
@@ -82,6 +86,9 @@ def main():
                 outputs2 = model(views[(t + 1) % len(views)]).float()
             if arm == "fused":
                 loss = loss_fn(outputs1.data, outputs2)                                # Contrastive_Learning.py:685-690
+            elif arm == "reference_bf16_inputs":
+                rb = lambda h: h + (h.bfloat16().float() - h).detach()
+                loss = reference_loss(rb(outputs1.data), rb(outputs2), a.temperature, rank, world)
             else:
                 loss = reference_loss(outputs1.data, outputs2, a.temperature, rank, world)
             Model_Util.learning_rate_schedule(sched)                                   # :693
@@ -97,15 +104,23 @@ def main():
         if arm == "fused":
             chained = loss_fn.chained_steps
     rel = [abs(x - y) / abs(x) for x, y in zip(curves["reference"], curves["fused"])]
+    rel_floor = [abs(x - y) / abs(x) for x, y in zip(curves["reference"], curves["reference_again"])]
+    rel_bf16 = [abs(x - y) / abs(x) for x, y in zip(curves["reference"], curves["reference_bf16_inputs"])]
     res = dict(config=dict(model="torchvision resnet50 + MLP(2048,%d,128), bf16 autocast" % a.hidden, batch_per_gpu=b, n_gpus=world,
                            image=a.image, steps=a.steps, temperature=a.temperature, optimizer="lars (Adam inside LARC mirror)",
                            lr_schedule="Model_Util.learning_rate_schedule mirror: linear scaling, 1 warm-up epoch, cosine",
                            fused_arm="NTXentLoss(chain_views=True, key_grad=False)", chained_steps=chained),
                loss_first=(curves["reference"][0], curves["fused"][0]), loss_last=(curves["reference"][-1], curves["fused"][-1]),
-               max_rel_diff=max(rel), mean_rel_diff=sum(rel) / len(rel), curves=curves)
+               max_rel_diff=max(rel), mean_rel_diff=sum(rel) / len(rel),
+               noise_floor_reference_vs_reference=dict(max_rel_diff=max(rel_floor), mean_rel_diff=sum(rel_floor) / len(rel_floor),
+                                                       loss_last=curves["reference_again"][-1]),
+               sensitivity_reference_with_bf16_rounded_inputs=dict(max_rel_diff=max(rel_bf16), mean_rel_diff=sum(rel_bf16) / len(rel_bf16),
+                                                                   loss_last=curves["reference_bf16_inputs"][-1]),
+               curves=curves)
     if rank == 0:
         for t in range(0, a.steps, max(1, a.steps // 10)):
-            print(f"step {t:4d}: reference {curves['reference'][t]:.5f}  fused {curves['fused'][t]:.5f}")
+            print(f"step {t:4d}: reference {curves['reference'][t]:.5f}  fused {curves['fused'][t]:.5f}  "
+                  f"reference again {curves['reference_again'][t]:.5f}  reference on bf16-rounded inputs {curves['reference_bf16_inputs'][t]:.5f}")
         print(json.dumps({k: v for k, v in res.items() if k != "curves"}))
         if a.out:
             json.dump(res, open(a.out, "w"), indent=1)
