@@ -142,6 +142,40 @@ def gather_row_factors(r_col: torch.Tensor, rank: int, b: int, world: int, group
     return r_col
 
 
+class SetReusePolicy:
+    """Which of NBUF peer-written buffer sets a forward may take, decided from the local issue order of forwards
+    and backwards (pure host logic; PeerWorkspace's docstring has the argument).  Every rank runs the same program,
+    so every rank reaches the same decisions."""
+
+    def __init__(self, nbuf: int):
+        self.nbuf = nbuf
+        self.step = 0                           # forwards issued so far
+        self.bwd_pending = [False] * nbuf       # the set's last forward still waits for its backward
+        self.bwd_stamp = [-1] * nbuf            # self.step at the time that backward was issued
+
+    def next_set(self, needs_bwd: bool):
+        """Returns (set index, extra_barrier) for the forward being issued; raises when the set's previous
+        backward is still outstanding.  extra_barrier: that backward was issued after the previous forward, so
+        the peers' synchronisation of the previous step does not cover it: a barrier must precede the first store."""
+        t = self.step
+        i = t % self.nbuf
+        if self.bwd_pending[i]:
+            raise RuntimeError(
+                f"maai NT-Xent: {self.nbuf} forward passes through the peer-gather workspace are waiting for "
+                f"their backward; at most {self.nbuf - 1} may be in flight (the next forward would overwrite "
+                "buffers a backward still reads, on this or another rank). Call backward first, or pass "
+                "peer_gather=False to use the NCCL all-gather path")
+        extra = self.bwd_stamp[i] >= t
+        self.step = t + 1
+        self.bwd_pending[i] = bool(needs_bwd)
+        self.bwd_stamp[i] = -1
+        return i, extra
+
+    def backward_issued(self, i: int):
+        self.bwd_pending[i] = False
+        self.bwd_stamp[i] = self.step
+
+
 class PeerWorkspace:
     """Symmetric (peer-mapped over NVLink) buffers for the fused gathers of the multi-GPU path.
 
@@ -222,9 +256,7 @@ class PeerWorkspace:
             mc = 0
         self.mc_z = [mc + o if mc else None for o in self.off_z]
         self.mc_r = [mc + o if mc else None for o in self.off_r]
-        self.step = 0                                    # forwards issued so far
-        self.bwd_pending = [False] * self.NBUF           # set's last forward still waits for its backward
-        self.bwd_stamp = [-1] * self.NBUF                # self.step at the time that backward was issued
+        self.policy = SetReusePolicy(self.NBUF)
         torch.cuda.synchronize(device)
         self.hdl.barrier(channel=0)                      # every rank's zero fill is done before first use
 
@@ -242,23 +274,8 @@ class PeerWorkspace:
         return ws
 
     def next_set(self, needs_bwd: bool):
-        """Set for the forward being issued (see the class docstring for the reuse rule).  Returns
-        (set index, extra_barrier): extra_barrier = a barrier must precede this forward's first store."""
-        t = self.step
-        i = t % self.NBUF
-        if self.bwd_pending[i]:
-            raise RuntimeError(
-                f"maai NT-Xent: {self.NBUF} forward passes through the peer-gather workspace are waiting for "
-                f"their backward; at most {self.NBUF - 1} may be in flight (the next forward would overwrite "
-                "buffers a backward still reads, on this or another rank). Call backward first, or pass "
-                "peer_gather=False to use the NCCL all-gather path")
-        # the set's previous backward was issued after the forward of step t-1 had been issued: the peers'
-        # barriers of step t-1 do not cover it
-        extra = self.bwd_stamp[i] >= t
-        self.step = t + 1
-        self.bwd_pending[i] = bool(needs_bwd)
-        self.bwd_stamp[i] = -1
-        return i, extra
+        """Set for the forward being issued (see the class docstring): (set index, extra_barrier)."""
+        return self.policy.next_set(needs_bwd)
 
     def sync_for(self, seq: int):
         """maai_peer_sync for step `seq` (None when barrier launches are used instead)."""
@@ -267,8 +284,7 @@ class PeerWorkspace:
         return _lib.PeerSync(self.f_tab.data_ptr(), self.flags.data_ptr(), self.counter.data_ptr(), seq, self.timeout_s)
 
     def backward_issued(self, i: int):
-        self.bwd_pending[i] = False
-        self.bwd_stamp[i] = self.step
+        self.policy.backward_issued(i)
 
 
 _peer_state = {"ok": None}

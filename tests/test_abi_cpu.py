@@ -111,3 +111,16 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no CPU or PyTorch fallback", ""), f"{f} mentions oracle"
+
+
+def test_integration_doc_stub_matches_the_abi():
+    """INTEGRATION.md shows the ctypes stub a maintainer would write: its argument lists must have the length of
+    the real signatures (the ABI changed three times this round; the doc must not drift)."""
+    import re
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    found = dict(re.findall(r"lib\.(maai_\w+)\.argtypes\s*=\s*\[([^\]]*)\]", text))
+    assert {"maai_ntxent_normalize", "maai_ntxent_fwd", "maai_ntxent_bwd"} <= set(found)
+    for name, args in found.items():
+        n_doc = len([a for a in args.split(",") if a.strip()])
+        assert n_doc == len(_lib.SIGNATURES[name][1]), (name, n_doc, len(_lib.SIGNATURES[name][1]))
+    assert f"ABI v{_lib.ABI_VERSION}" in text

@@ -102,3 +102,46 @@ def test_cross_rank_symmetric_forward_switch(monkeypatch):
     assert _sym_forward_enabled(64, 128, 8) and not _sym_forward_enabled(64, 128, 32)
     monkeypatch.setenv("MAAI_FWD_SYM_MULTI", "0")
     assert not _sym_forward_enabled(16384, 128, 2)
+
+
+def test_peer_buffer_set_reuse_policy():
+    """PeerWorkspace's reuse rule as pure host logic (SetReusePolicy): which issue orders of forwards / backwards
+    are free, which need the extra barrier, which must raise (a rank racing ahead must never overwrite
+    a set another rank's backward still reads)."""
+    import pytest
+    from maai_b200.Objective import SetReusePolicy
+    # f b f b ...: never an extra barrier, sets in turn
+    p = SetReusePolicy(3)
+    for t in range(9):
+        i, extra = p.next_set(True)
+        assert (i, extra) == (t % 3, False)
+        p.backward_issued(i)
+    # two in flight: f0 f1 b1 b0 f2 f3 b3 b2 f4 f5 b5 b4 -- what three sets buy: still no extra barrier
+    p = SetReusePolicy(3)
+    for rep in range(4):
+        (a, ea), (b, eb) = p.next_set(True), p.next_set(True)
+        assert not ea and not eb
+        p.backward_issued(b); p.backward_issued(a)
+    # three in flight: the fourth forward must raise; after the backwards the set is reusable, but its backward
+    # came after the previous forward was issued -> extra barrier
+    p = SetReusePolicy(3)
+    sets = [p.next_set(True)[0] for _ in range(3)]
+    with pytest.raises(RuntimeError):
+        p.next_set(True)
+    assert p.step == 3  # the refused forward was not counted
+    for i in reversed(sets):
+        p.backward_issued(i)
+    i, extra = p.next_set(True)
+    assert i == 0 and extra
+    p.backward_issued(i)
+    i, extra = p.next_set(True)   # set 1: its backward was issued before the previous forward (step 3) -> free
+    assert i == 1 and not extra
+    # forward-only calls (no_grad) never block a set
+    p = SetReusePolicy(3)
+    for t in range(10):
+        assert p.next_set(False) == (t % 3, False)
+    # with two sets (round 1) the advisor's pattern f0 f1 b1 b0 f2 needs the extra barrier
+    p = SetReusePolicy(2)
+    a, b = p.next_set(True)[0], p.next_set(True)[0]
+    p.backward_issued(b); p.backward_issued(a)
+    assert p.next_set(True) == (0, True)
