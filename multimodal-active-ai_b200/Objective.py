@@ -145,35 +145,43 @@ def gather_row_factors(r_col: torch.Tensor, rank: int, b: int, world: int, group
 class SetReusePolicy:
     """Which of NBUF peer-written buffer sets a forward may take, decided from the local issue order of forwards
     and backwards (pure host logic; PeerWorkspace's docstring has the argument).  Every rank runs the same program,
-    so every rank reaches the same decisions."""
+    so every rank reaches the same decisions.  The state lives in one int64 array -- [0] forwards issued so far,
+    [1 .. nbuf] "the set's last forward still waits for its backward", [1 + nbuf ..] forwards issued at the time
+    that backward was issued (-1: none yet) -- so that the C++ binding's backward (csrc/maai_torch_ext.cpp, which
+    runs on the autograd engine's thread) can mark its set through the array's address."""
 
     def __init__(self, nbuf: int):
+        import numpy as np
         self.nbuf = nbuf
-        self.step = 0                           # forwards issued so far
-        self.bwd_pending = [False] * nbuf       # the set's last forward still waits for its backward
-        self.bwd_stamp = [-1] * nbuf            # self.step at the time that backward was issued
+        self.state = np.zeros(1 + 2 * nbuf, dtype=np.int64)
+        self.state[1 + nbuf:] = -1
+
+    @property
+    def step(self) -> int:
+        return int(self.state[0])
 
     def next_set(self, needs_bwd: bool):
         """Returns (set index, extra_barrier) for the forward being issued; raises when the set's previous
         backward is still outstanding.  extra_barrier: that backward was issued after the previous forward, so
         the peers' synchronisation of the previous step does not cover it: a barrier must precede the first store."""
-        t = self.step
-        i = t % self.nbuf
-        if self.bwd_pending[i]:
+        st, n = self.state, self.nbuf
+        t = int(st[0])
+        i = t % n
+        if st[1 + i]:
             raise RuntimeError(
-                f"maai NT-Xent: {self.nbuf} forward passes through the peer-gather workspace are waiting for "
-                f"their backward; at most {self.nbuf - 1} may be in flight (the next forward would overwrite "
+                f"maai NT-Xent: {n} forward passes through the peer-gather workspace are waiting for "
+                f"their backward; at most {n - 1} may be in flight (the next forward would overwrite "
                 "buffers a backward still reads, on this or another rank). Call backward first, or pass "
                 "peer_gather=False to use the NCCL all-gather path")
-        extra = self.bwd_stamp[i] >= t
-        self.step = t + 1
-        self.bwd_pending[i] = bool(needs_bwd)
-        self.bwd_stamp[i] = -1
+        extra = bool(st[1 + n + i] >= t)
+        st[0] = t + 1
+        st[1 + i] = 1 if needs_bwd else 0
+        st[1 + n + i] = -1
         return i, extra
 
     def backward_issued(self, i: int):
-        self.bwd_pending[i] = False
-        self.bwd_stamp[i] = self.step
+        self.state[1 + i] = 0
+        self.state[1 + self.nbuf + i] = self.state[0]
 
 
 class PeerWorkspace:
@@ -257,6 +265,7 @@ class PeerWorkspace:
         self.mc_z = [mc + o if mc else None for o in self.off_z]
         self.mc_r = [mc + o if mc else None for o in self.off_r]
         self.policy = SetReusePolicy(self.NBUF)
+        self._fast = None
         torch.cuda.synchronize(device)
         self.hdl.barrier(channel=0)                      # every rank's zero fill is done before first use
 
@@ -276,6 +285,17 @@ class PeerWorkspace:
     def next_set(self, needs_bwd: bool):
         """Set for the forward being issued (see the class docstring): (set index, extra_barrier)."""
         return self.policy.next_set(needs_bwd)
+
+    def fast_args(self, i: int, seq: int):
+        """Argument vector of the C++ binding's multi-rank step (csrc/maai_torch_ext.cpp, enum PeerArg) for set i."""
+        if self._fast is None:
+            self._fast = [[self.rank, self.world, self.z[k].data_ptr(), self.z_tab[k].data_ptr(), self.mc_z[k] or 0,
+                           self.r[k].data_ptr(), self.r_tab[k].data_ptr(), self.mc_r[k] or 0, self.f_tab.data_ptr(),
+                           self.flags.data_ptr(), self.counter.data_ptr(), 0, self.timeout_s, k, self.NBUF,
+                           int(self.policy.state.ctypes.data)] for k in range(self.NBUF)]
+        a = self._fast[i]
+        a[11] = seq
+        return a
 
     def sync_for(self, seq: int):
         """maai_peer_sync for step `seq` (None when barrier launches are used instead)."""
@@ -735,11 +755,14 @@ def contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0, local_
         else:
             peer = bool(peer_gather)
     ext = None
-    if int(world_size) == 1 and stash is None and _carry is None and not _Profiler.enabled:
+    loss = None
+    if stash is None and _carry is None and _chain is None and not _Profiler.enabled:
         ext = _lib.fast_ext()  # C++ autograd binding of the same C-ABI calls (host cost only)
-    if ext is not None:
+    if ext is not None and int(world_size) == 1:
         loss = ext.ntxent_loss(hidden1, hidden2, float(temperature))
-    else:
+    elif ext is not None and peer and key_grad is True:
+        loss = _peer_fast(ext, hidden1, hidden2, float(temperature), int(local_rank), int(world_size), group)
+    if loss is None:
         loss = _NTXentFunction.apply(hidden1, hidden2, float(temperature), int(local_rank),
                                      int(world_size), group, key_grad, stash, peer, _chain, _carry)
     logits_ab = labels = None
@@ -747,6 +770,24 @@ def contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0, local_
         logits_ab, labels = _logits_and_labels(stash["z_all"], hidden1.shape[0], int(local_rank),
                                                int(world_size), float(temperature))
     return loss, logits_ab, labels
+
+
+def _peer_fast(ext, hidden1, hidden2, temperature, rank, world, group):
+    """The default multi-rank training call (peer gathers ordered by in-kernel flags, full gradient, no cross-rank
+    symmetric forward) through the C++ binding: Python only picks the buffer set.  None = not this case."""
+    b, d = hidden1.shape
+    dev = hidden1.device
+    dp = padded_dim(d)
+    ws = PeerWorkspace.get(b, dp, world, rank, dev, group)
+    if not ws.use_flags or _sym_forward_mode(b, dp, world, True) != "off":
+        return None
+    needs_grad = torch.is_grad_enabled() and (hidden1.requires_grad or hidden2.requires_grad)
+    i, extra_barrier = ws.next_set(needs_grad)
+    ws.seq += 1
+    if extra_barrier:  # the previous user of this set ran its backward late: see PeerWorkspace
+        with _on_device(dev):
+            ws.hdl.barrier(channel=0)
+    return ext.ntxent_loss_peer(hidden1, hidden2, temperature, ws.fast_args(i, ws.seq))
 
 
 def _logits_and_labels(z_all, b, rank, world, temperature):

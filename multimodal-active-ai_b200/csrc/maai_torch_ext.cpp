@@ -116,6 +116,115 @@ class NTXentFn : public torch::autograd::Function<NTXentFn> {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// Multi-rank step with the fused peer gathers ordered by in-kernel flags (full gradient, no cross-rank symmetric
+// forward, no chained views): the same three C-ABI calls as Objective.py::_forward_peer / backward.  The buffer
+// set, its peer tables and the flag block are chosen and owned by Python (PeerWorkspace); `a` carries their
+// addresses.  `state` is the host int64 array of PeerWorkspace's SetReusePolicy ([0] = forwards issued,
+// [1 .. nbuf] = backward pending per set, [1 + nbuf .. ] = stamp per set): the backward marks its set as issued
+// there, exactly like SetReusePolicy.backward_issued.
+enum PeerArg : int { A_RANK, A_WORLD, A_Z_ALL, A_Z_TAB, A_MC_Z, A_R_COL, A_R_TAB, A_MC_R, A_F_TAB, A_FLAGS, A_COUNTER,
+                     A_SEQ, A_TIMEOUT, A_SET, A_NBUF, A_STATE, A_COUNT };
+
+maai_peer_sync make_sync(const std::vector<int64_t>& a) {
+  maai_peer_sync s;
+  s.peer_flag_bases = reinterpret_cast<const void* const*>(a[A_F_TAB]);
+  s.local_flags = reinterpret_cast<unsigned int*>(a[A_FLAGS]);
+  s.counter = reinterpret_cast<unsigned int*>(a[A_COUNTER]);
+  s.seq = (unsigned int)a[A_SEQ];
+  s.timeout_s = (unsigned int)a[A_TIMEOUT];
+  return s;
+}
+
+class NTXentPeerFn : public torch::autograd::Function<NTXentPeerFn> {
+ public:
+  static torch::Tensor forward(torch::autograd::AutogradContext* ctx, torch::Tensor hidden1, torch::Tensor hidden2,
+                               double temperature, bool need_bwd, std::vector<int64_t> a) {
+    TORCH_CHECK((int)a.size() == A_COUNT, "ntxent_loss_peer: bad argument vector");
+    const auto h1 = hidden1.contiguous();
+    const auto h2 = hidden2.contiguous();
+    const int b = (int)h1.size(0), d = (int)h1.size(1);
+    const int rank = (int)a[A_RANK], world = (int)a[A_WORLD];
+    const int dp = maai_padded_dim(d);
+    TORCH_CHECK_VALUE(dp > 0, "embedding dim ", d, " unsupported: the sm_100a tile kernels take 1 <= d <= 256");
+    const int dt = dtype_code(h1);
+    const float inv_tau = (float)(1.0 / temperature);
+    c10::cuda::CUDAGuard guard(h1.device());
+    void* st = at::cuda::getCurrentCUDAStream(h1.device().index()).stream();
+    // one fp32 allocation: [step workspace] (zero-filled by K1) | inv_norm | pos_cos
+    Layout l = make_layout(b, dp, need_bwd);
+    l.r_len = 0;  // the gathered row factors live in the peer-mapped set, not here
+    l.off_inv = (l.ws_words + 3) / 4 * 4;
+    l.off_cos = l.off_inv + 2 * b;
+    l.total = l.off_cos + b;
+    auto buf = torch::empty({l.total}, h1.options().dtype(torch::kFloat32));
+    auto loss = torch::empty({}, h1.options().dtype(torch::kFloat32));
+    float* base = buf.data_ptr<float>();
+    const maai_peer_sync sync = make_sync(a);
+    check_rc(maai_ntxent_normalize_peer(h1.data_ptr(), h2.data_ptr(), b, d, dt,
+                                        reinterpret_cast<const void* const*>(a[A_Z_TAB]), reinterpret_cast<void*>(a[A_MC_Z]),
+                                        world, rank, base + l.off_inv, base + l.off_cos, base, (size_t)l.ws_words * 4, &sync, st),
+             "maai_ntxent_normalize_peer");
+    check_rc(maai_ntxent_fwd_peer(reinterpret_cast<const void*>(a[A_Z_ALL]), b, world, rank, dp, inv_tau, base + l.off_cos, base,
+                                  reinterpret_cast<const void* const*>(a[A_R_TAB]), reinterpret_cast<void*>(a[A_MC_R]),
+                                  loss.data_ptr<float>(), MAAI_F_PREZEROED, &sync, st),
+             "maai_ntxent_fwd_peer");
+    if (need_bwd) {
+      ctx->save_for_backward({h1, h2});
+      ctx->saved_data["buf"] = buf;
+      ctx->saved_data["a"] = a;
+      ctx->saved_data["inv_tau"] = (double)inv_tau;
+      ctx->saved_data["clean"] = true;
+    }
+    return loss;
+  }
+
+  static torch::autograd::variable_list backward(torch::autograd::AutogradContext* ctx,
+                                                 torch::autograd::variable_list grad_out) {
+    const auto saved = ctx->get_saved_variables();
+    const auto& h1 = saved[0];
+    const auto& h2 = saved[1];
+    const auto buf = ctx->saved_data["buf"].toTensor();
+    const std::vector<int64_t> a = ctx->saved_data["a"].toIntVector();
+    const float inv_tau = (float)ctx->saved_data["inv_tau"].toDouble();
+    const bool clean = ctx->saved_data["clean"].toBool();
+    ctx->saved_data["clean"] = false;
+    const int b = (int)h1.size(0), d = (int)h1.size(1);
+    const int rank = (int)a[A_RANK], world = (int)a[A_WORLD];
+    const int dp = maai_padded_dim(d);
+    const int need = (ctx->needs_input_grad(0) ? 1 : 0) | (ctx->needs_input_grad(1) ? 2 : 0);
+    c10::cuda::CUDAGuard guard(h1.device());
+    void* st = at::cuda::getCurrentCUDAStream(h1.device().index()).stream();
+    Layout l = make_layout(b, dp, true);
+    l.off_inv = (l.ws_words + 3) / 4 * 4;
+    l.off_cos = l.off_inv + 2 * b;
+    float* base = buf.data_ptr<float>();
+    auto g = grad_out[0].to(h1.device(), torch::kFloat32).contiguous();
+    torch::Tensor dh1, dh2;
+    if (need & 1) dh1 = torch::empty_like(h1);
+    if (need & 2) dh2 = torch::empty_like(h2);
+    const maai_peer_sync sync = make_sync(a);
+    const float* r_col = reinterpret_cast<const float*>(a[A_R_COL]);
+    check_rc(maai_ntxent_bwd(reinterpret_cast<const void*>(a[A_Z_ALL]), r_col + (size_t)rank * 2 * b, r_col, 1, base,
+                             base + l.off_cos, h1.data_ptr(), h2.data_ptr(), dtype_code(h1), base + l.off_inv,
+                             g.data_ptr<float>(), b, world, rank, d, dp, inv_tau, need,
+                             (need & 1) ? dh1.data_ptr() : nullptr, (need & 2) ? dh2.data_ptr() : nullptr, base + l.head,
+                             clean ? MAAI_F_PREZEROED : 0, &sync, st),
+             "maai_ntxent_bwd");
+    // SetReusePolicy.backward_issued(set): every reader of the set is on the stream now
+    int64_t* state = reinterpret_cast<int64_t*>(a[A_STATE]);
+    const int64_t nbuf = a[A_NBUF], set = a[A_SET];
+    state[1 + set] = 0;
+    state[1 + nbuf + set] = state[0];
+    return {dh1, dh2, torch::Tensor(), torch::Tensor(), torch::Tensor()};
+  }
+};
+
+torch::Tensor ntxent_loss_peer(torch::Tensor hidden1, torch::Tensor hidden2, double temperature, std::vector<int64_t> a) {
+  const bool need_bwd = torch::GradMode::is_enabled() && (hidden1.requires_grad() || hidden2.requires_grad());
+  return NTXentPeerFn::apply(hidden1, hidden2, temperature, need_bwd, a);
+}
+
 torch::Tensor ntxent_loss(torch::Tensor hidden1, torch::Tensor hidden2, double temperature) {
   const bool need_bwd = torch::GradMode::is_enabled() && (hidden1.requires_grad() || hidden2.requires_grad());
   return NTXentFn::apply(hidden1, hidden2, temperature, need_bwd);
@@ -126,5 +235,7 @@ torch::Tensor ntxent_loss(torch::Tensor hidden1, torch::Tensor hidden2, double t
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "C++ autograd binding of the single-rank NT-Xent step over libmaai_ntxent.so";
   m.def("ntxent_loss", &ntxent_loss, "loss = NT-Xent(hidden1, hidden2) on one rank (Objective.py:17-81), autograd-aware");
+  m.def("ntxent_loss_peer", &ntxent_loss_peer,
+        "multi-rank loss with the fused peer gathers ordered by in-kernel flags (see NTXentPeerFn); the buffer set is the caller's");
   m.def("abi_version", [] { return maai_abi_version(); });
 }
