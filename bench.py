@@ -424,7 +424,7 @@ def main():
             t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             total_ms = float(t)
-        spans = {k: [a.elapsed_time(e) for a, e in v] for k, v in _Profiler.events.items()}
+        spans = _Profiler.collect_ms()
         if profile and world > 1:  # every rank's own view (stderr): a rank that waits for a peer shows it here
             sys.stderr.write(f"[rank {rank}] step ms mean {sum(ms) / steps:.4f} median {statistics.median(ms):.4f} "
                              f"max {max(ms):.4f}; spans " +
@@ -510,6 +510,7 @@ def main():
         keep = [None] * NSLOT  # the slot's device results stay referenced until their D2H copy has been consumed
         e2e_host["t0"] = time.perf_counter()
         e2e_host["spans"] = []
+        e2e_host["blocked_s"] = 0.0  # host time spent WAITING for the device (slot reuse), not issuing
 
         def h2d(i):
             s_ = i % NSLOT
@@ -536,7 +537,9 @@ def main():
             e2e_host.setdefault("spans", []).append((c0, c1))
             ev_done[s_].record(main_s)
             if i >= NSLOT:
+                tb = time.perf_counter()
                 ev_out[s_].synchronize()  # the host has consumed this slot's previous results
+                e2e_host["blocked_s"] += time.perf_counter() - tb
             keep[s_] = (loss, x, y)
             with torch.cuda.stream(out_s):
                 out_s.wait_event(ev_done[s_])
@@ -574,6 +577,7 @@ def main():
 
     e2e_pipelined(args.warmup)
     e2e_pipe_s = timed_e2e(e2e_pipelined)  # first: same clock regime as the device-resident run just before
+    e2e_pipe_blocked_s = e2e_host.get("blocked_s", 0.0)
     e2e_compute_ms = statistics.mean(a.elapsed_time(e) for a, e in e2e_host["spans"]) if e2e_host.get("spans") else None
     for _ in range(args.warmup):
         e2e_serial_step()
@@ -701,6 +705,7 @@ def main():
                     "schedule": e2e_mode, "loss_read_on_host": e2e_loss,
                     "pipelined_ms_per_step": e2e_pipe_s / args.steps * 1e3,
                     "pipelined_host_issue_ms_per_step": e2e_host.get("issue_s", 0.0) / args.steps * 1e3,
+                    "pipelined_host_blocked_ms_per_step": e2e_pipe_blocked_s / args.steps * 1e3,
                     "pipelined_compute_span_ms": e2e_compute_ms,
                     "copies_only_ms_per_step": copy_floor_s / args.steps * 1e3,
                     "copies_only_note": "the same H2D + D2H bytes per step on the two copy streams with NO compute, all ranks "

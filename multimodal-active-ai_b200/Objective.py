@@ -45,10 +45,36 @@ class _Profiler:
     events = {"normalize": [], "gather_z": [], "fwd": [], "gather_l": [], "finalize": [], "gather_r": [], "bwd": [],
               "bwd_keyside": [], "reduce_scatter_wait": [], "bwd_dh": []}
 
+    _ext = None      # the C++ binding keeps its own brackets (same names) once a call has gone through it
+    _ext_on = False
+
     @classmethod
     def reset(cls):
         for v in cls.events.values():
             v.clear()
+        if cls._ext is not None:
+            cls._ext.span_reset()
+
+    @classmethod
+    def sync_ext(cls, ext):
+        if cls._ext is None:
+            cls._ext = ext
+        if cls._ext_on != cls.enabled:
+            ext.span_timing(bool(cls.enabled))
+            cls._ext_on = bool(cls.enabled)
+
+    @classmethod
+    def collect_ms(cls):
+        """{span name: [ms per bracketed call]} over the Python path's and the C++ binding's brackets (synchronises)."""
+        out = {}
+        for k, v in cls.events.items():
+            if v:
+                v[-1][1].synchronize()
+            out[k] = [a.elapsed_time(e) for a, e in v]
+        if cls._ext is not None:
+            for k, ms in zip(("normalize", "fwd", "bwd"), cls._ext.span_read()):
+                out[k] = out[k] + list(ms)
+        return out
 
     class span:
         def __init__(self, name):
@@ -756,8 +782,10 @@ def contrastive_loss(hidden1, hidden2, hidden_norm=True, temperature=1.0, local_
             peer = bool(peer_gather)
     ext = None
     loss = None
-    if stash is None and _carry is None and _chain is None and not _Profiler.enabled:
+    if stash is None and _carry is None and _chain is None:
         ext = _lib.fast_ext()  # C++ autograd binding of the same C-ABI calls (host cost only)
+        if ext is not None and (_Profiler.enabled or _Profiler._ext_on):
+            _Profiler.sync_ext(ext)
     if ext is not None and int(world_size) == 1:
         loss = ext.ntxent_loss(hidden1, hidden2, float(temperature))
     elif ext is not None and peer and key_grad is True:

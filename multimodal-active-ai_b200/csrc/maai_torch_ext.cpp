@@ -1,4 +1,4 @@
-// C++ autograd binding of the single-rank NT-Xent step (plumbing, not the product: every kernel it
+// C++ autograd binding of the NT-Xent step, single-rank and multi-rank with peer gathers (plumbing, not the product: every kernel it
 // enqueues lives in libmaai_ntxent.so behind include/maai_ntxent.h).
 //
 // Why it exists: at the batch sizes the reference trains with (256 - 4096 pairs per GPU,
@@ -11,6 +11,10 @@
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
+
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "../../include/maai_ntxent.h"
 
@@ -32,6 +36,54 @@ void check_rc(int rc, const char* what) {
   TORCH_CHECK_VALUE(rc != MAAI_E_ARG && rc != MAAI_E_SHAPE, msg);
   TORCH_CHECK(false, msg);
 }
+
+// Optional CUDA-event brackets around the three C-ABI calls of a step (bench.py's live per-kernel timing; the
+// Python path has the same brackets in Objective.py::_Profiler).  Off by default: two cudaEventRecord per call.
+namespace spans {
+enum Kind { NORMALIZE, FWD, BWD, KINDS };
+std::mutex mu;  // forward runs on the caller's thread, backward on the autograd engine's
+bool on = false;
+std::vector<cudaEvent_t> pool;
+size_t used = 0;
+std::vector<std::pair<size_t, size_t>> rec[KINDS];
+
+long mark(void* stream) {
+  std::lock_guard<std::mutex> g(mu);
+  if (!on) return -1;
+  if (used == pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return -1;
+    pool.push_back(e);
+  }
+  cudaEventRecord(pool[used], static_cast<cudaStream_t>(stream));
+  return (long)used++;
+}
+void add(Kind k, long a, long b) {
+  if (a < 0 || b < 0) return;
+  std::lock_guard<std::mutex> g(mu);
+  rec[k].emplace_back((size_t)a, (size_t)b);
+}
+void enable(bool v) {
+  std::lock_guard<std::mutex> g(mu);
+  on = v;
+}
+void reset() {
+  std::lock_guard<std::mutex> g(mu);
+  used = 0;
+  for (auto& r : rec) r.clear();
+}
+std::vector<std::vector<double>> read() {  // ms per recorded call: [normalize, fwd, bwd]; waits for the events
+  std::lock_guard<std::mutex> g(mu);
+  std::vector<std::vector<double>> out(KINDS);
+  for (int k = 0; k < KINDS; ++k)
+    for (const auto& ab : rec[k]) {
+      float ms = 0.f;
+      cudaEventSynchronize(pool[ab.second]);
+      if (cudaEventElapsedTime(&ms, pool[ab.first], pool[ab.second]) == cudaSuccess) out[k].push_back(ms);
+    }
+  return out;
+}
+}  // namespace spans
 
 struct Layout {  // one fp32 allocation: [step workspace | r_col] (zero-filled by K1) | inv_norm | pos_cos
   int64_t ws_words, head, r_len, off_r, off_inv, off_cos, total;
@@ -68,12 +120,18 @@ class NTXentFn : public torch::autograd::Function<NTXentFn> {
     // the loss is its own tensor: an output that is a view of a buffer created in here gets no grad_fn
     auto loss = torch::empty({}, h1.options().dtype(torch::kFloat32));
     float* base = buf.data_ptr<float>();
+    const long e0 = spans::mark(st);
     check_rc(maai_ntxent_normalize(h1.data_ptr(), h2.data_ptr(), b, d, dt, z.data_ptr(), base + l.off_inv,
                                    base + l.off_cos, base, (size_t)(l.ws_words + l.r_len) * 4, st),
              "maai_ntxent_normalize");
+    const long e1 = spans::mark(st);
     check_rc(maai_ntxent_fwd(z.data_ptr(), b, 1, 0, dp, inv_tau, base + l.off_cos, base,
                              need_bwd ? base + l.off_r : nullptr, loss.data_ptr<float>(), MAAI_F_PREZEROED, nullptr, st),
              "maai_ntxent_fwd");
+    if (e0 >= 0) {
+      spans::add(spans::NORMALIZE, e0, e1);
+      spans::add(spans::FWD, e1, spans::mark(st));
+    }
     if (need_bwd) {
       ctx->save_for_backward({h1, h2});
       ctx->saved_data["z"] = z;
@@ -107,11 +165,13 @@ class NTXentFn : public torch::autograd::Function<NTXentFn> {
     torch::Tensor dh1, dh2;
     if (need & 1) dh1 = torch::empty_like(h1);
     if (need & 2) dh2 = torch::empty_like(h2);
+    const long e0 = spans::mark(st);
     check_rc(maai_ntxent_bwd(z.data_ptr(), base + l.off_r, base + l.off_r, 1, base, base + l.off_cos, h1.data_ptr(),
                              h2.data_ptr(), dtype_code(h1), base + l.off_inv, g.data_ptr<float>(), b, 1, 0, d, dp,
                              inv_tau, need, (need & 1) ? dh1.data_ptr() : nullptr, (need & 2) ? dh2.data_ptr() : nullptr,
                              base + l.head, clean ? MAAI_F_PREZEROED : 0, nullptr, st),
              "maai_ntxent_bwd");
+    if (e0 >= 0) spans::add(spans::BWD, e0, spans::mark(st));
     return {dh1, dh2, torch::Tensor(), torch::Tensor()};
   }
 };
@@ -161,14 +221,20 @@ class NTXentPeerFn : public torch::autograd::Function<NTXentPeerFn> {
     auto loss = torch::empty({}, h1.options().dtype(torch::kFloat32));
     float* base = buf.data_ptr<float>();
     const maai_peer_sync sync = make_sync(a);
+    const long e0 = spans::mark(st);
     check_rc(maai_ntxent_normalize_peer(h1.data_ptr(), h2.data_ptr(), b, d, dt,
                                         reinterpret_cast<const void* const*>(a[A_Z_TAB]), reinterpret_cast<void*>(a[A_MC_Z]),
                                         world, rank, base + l.off_inv, base + l.off_cos, base, (size_t)l.ws_words * 4, &sync, st),
              "maai_ntxent_normalize_peer");
+    const long e1 = spans::mark(st);
     check_rc(maai_ntxent_fwd_peer(reinterpret_cast<const void*>(a[A_Z_ALL]), b, world, rank, dp, inv_tau, base + l.off_cos, base,
                                   reinterpret_cast<const void* const*>(a[A_R_TAB]), reinterpret_cast<void*>(a[A_MC_R]),
                                   loss.data_ptr<float>(), MAAI_F_PREZEROED, &sync, st),
              "maai_ntxent_fwd_peer");
+    if (e0 >= 0) {
+      spans::add(spans::NORMALIZE, e0, e1);
+      spans::add(spans::FWD, e1, spans::mark(st));
+    }
     if (need_bwd) {
       ctx->save_for_backward({h1, h2});
       ctx->saved_data["buf"] = buf;
@@ -205,12 +271,14 @@ class NTXentPeerFn : public torch::autograd::Function<NTXentPeerFn> {
     if (need & 2) dh2 = torch::empty_like(h2);
     const maai_peer_sync sync = make_sync(a);
     const float* r_col = reinterpret_cast<const float*>(a[A_R_COL]);
+    const long e0 = spans::mark(st);
     check_rc(maai_ntxent_bwd(reinterpret_cast<const void*>(a[A_Z_ALL]), r_col + (size_t)rank * 2 * b, r_col, 1, base,
                              base + l.off_cos, h1.data_ptr(), h2.data_ptr(), dtype_code(h1), base + l.off_inv,
                              g.data_ptr<float>(), b, world, rank, d, dp, inv_tau, need,
                              (need & 1) ? dh1.data_ptr() : nullptr, (need & 2) ? dh2.data_ptr() : nullptr, base + l.head,
                              clean ? MAAI_F_PREZEROED : 0, &sync, st),
              "maai_ntxent_bwd");
+    if (e0 >= 0) spans::add(spans::BWD, e0, spans::mark(st));
     // SetReusePolicy.backward_issued(set): every reader of the set is on the stream now
     int64_t* state = reinterpret_cast<int64_t*>(a[A_STATE]);
     const int64_t nbuf = a[A_NBUF], set = a[A_SET];
@@ -238,4 +306,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ntxent_loss_peer", &ntxent_loss_peer,
         "multi-rank loss with the fused peer gathers ordered by in-kernel flags (see NTXentPeerFn); the buffer set is the caller's");
   m.def("abi_version", [] { return maai_abi_version(); });
+  m.def("span_timing", &spans::enable, "switch the CUDA-event brackets around normalize / fwd / bwd on or off");
+  m.def("span_reset", &spans::reset);
+  m.def("span_read", &spans::read, "ms per bracketed call since the last reset: [normalize, fwd, bwd]");
 }

@@ -40,7 +40,7 @@ for chained in (False, True):
         o1 = o2
     torch.cuda.synchronize()
     _Profiler.enabled = False
-    k1 = statistics.median(x.elapsed_time(y) for x, y in _Profiler.events["normalize"])
+    k1 = statistics.median(_Profiler.collect_ms()["normalize"])
     step = statistics.median(x.elapsed_time(y) for x, y in spans[5:])
     if rank == 0:
         print(f"W={world} b={b} chain_views={chained}: K1 span {k1 * 1e3:.1f} us, step (hidden1 detached) {step * 1e3:.1f} us, "

@@ -27,8 +27,8 @@ for i in range(iters + 5):
     loss, _, _ = maai_b200.contrastive_loss(x, y, temperature=tau, device="cuda")
     loss.backward()
 torch.cuda.synchronize()
-f = [a.elapsed_time(b) for a, b in _Profiler.events["fwd"]]
-w = [a.elapsed_time(b) for a, b in _Profiler.events["bwd"]]
+ms = _Profiler.collect_ms()
+f, w = ms["fwd"], ms["bwd"]
 fm, wm = statistics.median(f), statistics.median(w)
 fl = 24.0 * B * B * d
 print(f"{os.path.basename(os.environ.get('MAAI_DEBUG_LIB', 'default')):24s} B={B} d={d} fwd {fm:.4f} (min {min(f):.4f}) "
