@@ -694,6 +694,14 @@ def _validate(hidden1, hidden2, hidden_norm, temperature, world_size, local_rank
         raise NotImplementedError("hidden_norm=False is not supported by the fused sm_100a path "
                                   "(fixed-maximum logsumexp needs unit-norm rows); no reference "
                                   "caller uses it")
+    if torch.are_deterministic_algorithms_enabled():
+        # same contract as torch's own non-deterministic CUDA ops (at::globalContext().alertNotDeterministic)
+        msg = ("maai NT-Xent does not have a deterministic implementation: row sums and the gradient accumulator are "
+               "combined with fp32 atomics across CTAs (run-to-run differences <= 1e-6 relative, DESIGN.md section 3). "
+               "Use torch.use_deterministic_algorithms(True, warn_only=True) to run it anyway")
+        if not torch.is_deterministic_algorithms_warn_only_enabled():
+            raise RuntimeError(msg)
+        _warn_once("deterministic", msg)
     if not hidden1.is_cuda or not hidden2.is_cuda:
         raise RuntimeError("maai NT-Xent runs on CUDA (sm_100a) tensors only: there is no CPU fallback")
     if hidden1.dtype not in _DTYPES or hidden2.dtype not in _DTYPES:

@@ -103,6 +103,22 @@ def test_no_cpu_fallback_and_argument_validation():
         maai_b200.contrastive_loss(a, b, hidden_norm=False)
 
 
+def test_deterministic_mode_is_honoured():
+    """fp32 atomics across CTAs: like torch's own non-deterministic CUDA ops, raise under
+    torch.use_deterministic_algorithms(True) and warn once under warn_only."""
+    a, b = torch.randn(4, 8), torch.randn(4, 8)
+    try:
+        torch.use_deterministic_algorithms(True)
+        with pytest.raises(RuntimeError, match="deterministic implementation"):
+            maai_b200.contrastive_loss(a, b)
+        torch.use_deterministic_algorithms(True, warn_only=True)
+        with pytest.warns(UserWarning, match="deterministic implementation"):
+            with pytest.raises(RuntimeError, match="no CPU fallback"):
+                maai_b200.contrastive_loss(a, b)
+    finally:
+        torch.use_deterministic_algorithms(False)
+
+
 def test_product_never_imports_oracle():
     """The product path must not route through the oracle (or any CPU fallback)."""
     pkg = os.path.join(ROOT, "multimodal-active-ai_b200")
