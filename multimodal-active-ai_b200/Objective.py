@@ -205,6 +205,9 @@ class SetReusePolicy:
         st[1 + n + i] = -1
         return i, extra
 
+    def any_pending(self) -> bool:
+        return bool(self.state[1:1 + self.nbuf].any())
+
     def backward_issued(self, i: int):
         self.state[1 + i] = 0
         self.state[1 + self.nbuf + i] = self.state[0]
@@ -302,11 +305,20 @@ class PeerWorkspace:
         key = (b, dp, world, rank, str(device), id(group))
         ws = cls._cache.get(key)
         if ws is None:
-            # every rank sees the same sequence of shapes, so they evict the same (oldest) entry
-            while len(cls._cache) >= cls.MAX_CACHED:
-                cls._cache.pop(next(iter(cls._cache)))
+            cls._evict(cls._cache, cls.MAX_CACHED)
             ws = cls._cache[key] = cls(b, dp, world, rank, device, group)
         return ws
+
+    @staticmethod
+    def _evict(cache: dict, max_cached: int) -> None:
+        """Drop the oldest workspaces down to max_cached - 1 entries, but never one whose backward is outstanding:
+        the C++ binding's backward holds raw addresses of the set and of the policy state, not a reference.  Every
+        rank sees the same sequence of shapes and of forwards / backwards, so all ranks evict the same entries."""
+        while len(cache) >= max_cached:
+            victim = next((k for k, w in cache.items() if not w.policy.any_pending()), None)
+            if victim is None:
+                return
+            cache.pop(victim)
 
     def next_set(self, needs_bwd: bool):
         """Set for the forward being issued (see the class docstring): (set index, extra_barrier)."""

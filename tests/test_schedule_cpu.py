@@ -145,3 +145,31 @@ def test_peer_buffer_set_reuse_policy():
     a, b = p.next_set(True)[0], p.next_set(True)[0]
     p.backward_issued(b); p.backward_issued(a)
     assert p.next_set(True) == (0, True)
+
+
+def test_peer_workspace_eviction_spares_pending_backwards():
+    """A cached peer workspace is evicted oldest-first, but never while one of its sets waits for a backward (the C++
+    binding's backward holds raw addresses into it)."""
+    from types import SimpleNamespace
+    from maai_b200.Objective import PeerWorkspace, SetReusePolicy
+    mk = lambda: SimpleNamespace(policy=SetReusePolicy(3))
+    cache = {k: mk() for k in "abcd"}
+    i, _ = cache["a"].policy.next_set(True)      # a: forward issued, backward outstanding
+    PeerWorkspace._evict(cache, 4)
+    assert list(cache) == ["a", "c", "d"]        # b (oldest idle) went, a stayed
+    cache["a"].policy.backward_issued(i)
+    cache["e"] = mk()
+    PeerWorkspace._evict(cache, 4)
+    assert list(cache) == ["c", "d", "e"]
+    for w in cache.values():                     # everything pending: nothing is evicted, the cache grows by one
+        w.policy.next_set(True)
+    cache["f"] = mk(); cache["f"].policy.next_set(True)
+    PeerWorkspace._evict(cache, 4)
+    assert list(cache) == ["c", "d", "e", "f"]
+    # the C++ backward's direct writes (state[1+set] = 0, state[1+nbuf+set] = state[0]) are backward_issued
+    p, q = SetReusePolicy(3), SetReusePolicy(3)
+    for pol in (p, q):
+        pol.next_set(True); pol.next_set(True)
+    p.backward_issued(1)
+    q.state[1 + 1] = 0; q.state[1 + 3 + 1] = q.state[0]
+    assert (p.state == q.state).all() and p.any_pending() and q.state.dtype.itemsize == 8
